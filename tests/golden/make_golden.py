@@ -1,0 +1,35 @@
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(oracle/_ref/libadmm_ref.so, built by oracle/Makefile from /root/reference) on the parity scenarios.
+
+Run in the build container (needs /root/reference for the _ref build and the shipped meshes):
+    python tests/golden/make_golden.py
+Each <name>.npz holds the scene (inputs) and the reference's per-iteration x / z / u dumps, per-frame x / v
+and the hyperelastic optimiser state; the -m gpu tests and the oracle-port tests compare against them."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "admm-elastic-sca_b200", "pyhost"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import scenes  # noqa: E402
+from scenarios import RefAdapter, build_scenarios, run_scenario  # noqa: E402
+
+
+def main():
+    S = build_scenarios()
+    for name, sc in S.items():
+        ad = RefAdapter(sc["scene"])
+        res = run_scenario(ad, sc, dump=True)
+        ad.close()
+        scenes.save_scene(os.path.join(HERE, f"{name}.scene.npz"), sc["scene"])
+        np.savez_compressed(os.path.join(HERE, f"{name}.ref.npz"), **res)
+        sz = os.path.getsize(os.path.join(HERE, f"{name}.ref.npz")) / 1024
+        print(f"{name:14s} frames={sc['frames']} x_it{res['x_it'].shape} z_it{res['z_it'].shape} -> {sz:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,38 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and refuses to run without a CUDA device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import admm_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exists_and_exports_every_declared_symbol():
+    assert os.path.exists(admm_b200.LIB_PATH), "build with __graft_entry__.build()"
+    L = C.CDLL(admm_b200.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(admmb_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found in the header"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/admm_b200.h but not exported"
+    assert sorted(admm_b200.EXPORTS) == declared
+
+
+def test_version_string():
+    L = admm_b200.lib()
+    assert b"sm_100a" in L.admmb_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present; the failure path is exercised on the CPU-only box")
+    L = admm_b200.lib()
+    h = C.c_void_p()
+    rc = L.admmb_create(0, C.byref(h))
+    assert rc == -3  # ADMMB_E_CUDA
+    assert b"no CPU path" in L.admmb_last_error(None)
