@@ -473,6 +473,38 @@ extern "C" int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout
 	return admmb_download_xv(ctx, x3n_inout, v3n_inout);
 }
 
+// Diagnostics for "teacher-forced" parity tests: run exactly one half of an ADMM iteration on given inputs.
+extern "C" int admmb_debug_local_step(admmb_ctx *ctx, const double *x3n) {
+	CHECK_READY(ctx);
+	if (!x3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null x");
+	const size_t n3 = 3 * (size_t)ctx->n;
+	memcpy(ctx->h_pin, x3n, n3 * sizeof(double));
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p, ctx->h_pin, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	int rc = launch_permute_in(ctx, ctx->d_io.p, ctx->d_currx.p);
+	if (rc) return rc;
+	for (Batch &b : ctx->batches)
+		if ((rc = launch_local_step(ctx, b, ctx->d_currx.p, ctx->dt * ctx->dt))) return rc;
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ADMMB_OK;
+}
+
+extern "C" int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n) {
+	CHECK_READY(ctx);
+	if (!xbar3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null x_bar");
+	const size_t n3 = 3 * (size_t)ctx->n;
+	// M x_bar on the host exactly as System.cpp:47 (m_masses.asDiagonal() * x_bar), then permuted in
+	for (int i = 0; i < ctx->n; ++i)
+		for (int j = 0; j < 3; ++j) ctx->h_pin[3 * (size_t)i + j] = ctx->h_m[i] * xbar3n[3 * (size_t)i + j];
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p, ctx->h_pin, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	int rc = launch_permute_in(ctx, ctx->d_io.p, ctx->d_Mxbar.p);
+	if (rc) return rc;
+	if ((rc = launch_rhs(ctx))) return rc;
+	rc = (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_solve(ctx) : direct_solve(ctx);
+	if (rc) return rc;
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ADMMB_OK;
+}
+
 extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
 	CHECK_READY(ctx);
 	if (admm_iters < 0 || frames < 1) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step_resident: bad arguments");

@@ -123,7 +123,7 @@ struct PcgSolver {
 	DevBuf<double> val, dinv;
 	DevBuf<double> r, p, Ap;
 	DevBuf<double> scal; // [0..5] pAp[2][3], [6..11] rz[2][3], [12..17] rr[2][3], [18..20] bb[3]
-	DevBuf<int> flag;    // [0] done, [1] iterations used
+	DevBuf<int> flag;    // [0] done, [1] iterations used, [2] iterations without progress
 	int *h_flag = nullptr;
 	int grid = 0;
 };
@@ -188,6 +188,7 @@ __global__ void k_pcg_check0(double *scal, int *flag, double tol2) {
 	for (int j = 0; j < 3; ++j) done = done && (scal[12 + j] <= tol2 * scal[18 + j]);
 	flag[0] = done ? 1 : 0;
 	flag[1] = 0;
+	flag[2] = 0;
 }
 
 // Ap = A p; pAp[k&1] += p.Ap; zero the accumulators the rest of this iteration adds into
@@ -262,6 +263,10 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int n, int k, con
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		scal[3 * nxt + 0] = 0.0; scal[3 * nxt + 1] = 0.0; scal[3 * nxt + 2] = 0.0;
 		flag[1] = k + 1;
+		// stagnation guard: once the residual sits at rounding level CG must not be iterated further
+		const double rr = scal[12 + 3 * nxt] + scal[12 + 3 * nxt + 1] + scal[12 + 3 * nxt + 2];
+		if (k == 0 || rr < 0.99 * scal[21]) { scal[21] = rr; flag[2] = 0; }
+		else if (++flag[2] >= 25 || !(rr == rr)) flag[0] = 1;
 	}
 	if (done && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) flag[0] = 1;
 }
@@ -285,7 +290,7 @@ int pcg_setup(admmb_ctx *ctx) {
 	ADMMB_CUDA(ctx, S.p.alloc(3 * (size_t)n));
 	ADMMB_CUDA(ctx, S.Ap.alloc(3 * (size_t)n));
 	ADMMB_CUDA(ctx, S.scal.alloc(24));
-	ADMMB_CUDA(ctx, S.flag.alloc(2));
+	ADMMB_CUDA(ctx, S.flag.alloc(4));
 	if (!S.h_flag) ADMMB_CUDA(ctx, cudaMallocHost((void **)&S.h_flag, 2 * sizeof(int)));
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);

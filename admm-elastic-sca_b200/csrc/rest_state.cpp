@@ -1,6 +1,7 @@
 // rest_state.cpp -- host-side restatement of the reference's Force::initialize() bodies: rest shapes,
 // volumes / areas and the (float-rounded) ADMM weights.  Runs once in admmb_finalize().  Citations are to
 // /root/reference/deps/admm-elastic-sca/src/system (A/src/system).
+#include <algorithm>
 #include <cmath>
 
 #include "common.h"
@@ -167,6 +168,22 @@ int compute_rest_state(admmb_ctx *ctx, Batch &b) {
 		break;
 	default:
 		ADMMB_FAIL(ctx, ADMMB_E_ARG, "unknown batch type %d", b.type);
+	}
+	// Corner order.  The reference forms Dx = m_D * curr_x with Eigen's column-major sparse product
+	// (System.cpp:54, SparseDenseProduct.h:190-209): every row accumulates its terms in ascending COLUMN, i.e.
+	// ascending node index.  D_i x is symmetric in the corners, so we store each tet / triangle with its corners
+	// sorted by node index; the kernels' left-to-right sums then round exactly like the reference's Dx.
+	if (b.type == BT_TETS || b.type == BT_TRIS) {
+		const int nv = b.nv, per = b.nsel / b.nv;
+		for (int e = 0; e < b.count; ++e) {
+			int *id = &b.idx[(size_t)e * nv];
+			double *S = &b.S[(size_t)e * b.nsel];
+			for (int a = 1; a < nv; ++a)          // insertion sort of <= 4 corners, rows of S move with them
+				for (int c = a; c > 0 && id[c - 1] > id[c]; --c) {
+					std::swap(id[c - 1], id[c]);
+					for (int k = 0; k < per; ++k) std::swap(S[(c - 1) * per + k], S[c * per + k]);
+				}
+		}
 	}
 	return ADMMB_OK;
 }

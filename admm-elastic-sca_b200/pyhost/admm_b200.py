@@ -23,7 +23,7 @@ EXPORTS = [
     "admmb_create", "admmb_destroy", "admmb_last_error", "admmb_version", "admmb_set_nodes", "admmb_add_tets",
     "admmb_add_tris", "admmb_add_springs", "admmb_add_bends", "admmb_add_static_anchors", "admmb_add_moving_anchors",
     "admmb_add_collision", "admmb_set_gravity", "admmb_set_solver", "admmb_finalize", "admmb_step",
-    "admmb_step_dump", "admmb_step_resident", "admmb_upload_xv", "admmb_download_xv", "admmb_update_anchor_targets",
+    "admmb_step_dump", "admmb_debug_local_step", "admmb_debug_global_step", "admmb_step_resident", "admmb_upload_xv", "admmb_download_xv", "admmb_update_anchor_targets",
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read",
@@ -66,6 +66,8 @@ def lib():
     L.admmb_finalize.argtypes = [vp, C.c_double]
     L.admmb_step.argtypes = [vp, C.c_int, _dp, _dp]
     L.admmb_step_dump.argtypes = [vp, C.c_int, _dp, _dp, vp, vp, vp]
+    L.admmb_debug_local_step.argtypes = [vp, _dp]
+    L.admmb_debug_global_step.argtypes = [vp, _dp]
     L.admmb_step_resident.argtypes = [vp, C.c_int, C.c_int]
     L.admmb_upload_xv.argtypes = [vp, vp, vp]
     L.admmb_download_xv.argtypes = [vp, vp, vp]
@@ -205,6 +207,12 @@ class System:
         self._ck(self.L.admmb_step_dump(self.h, K, self.m_x, self.m_v, xi.ctypes.data_as(C.c_void_p),
                                         zi.ctypes.data_as(C.c_void_p), ui.ctypes.data_as(C.c_void_p)))
         return xi, zi, ui
+
+    def debug_local_step(self, x):
+        self._ck(self.L.admmb_debug_local_step(self.h, _f64(x).reshape(-1)))
+
+    def debug_global_step(self, xbar):
+        self._ck(self.L.admmb_debug_global_step(self.h, _f64(xbar).reshape(-1)))
 
     def step_resident(self, frames=1, iters=None):
         self._ck(self.L.admmb_step_resident(self.h, int(self.admm_iters if iters is None else iters), int(frames)))

@@ -109,6 +109,12 @@ int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_in
 int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout, double *x_it,
                     double *z_it, double *u_it);
 
+/* Diagnostics for teacher-forced parity tests: one half of an ADMM iteration on caller-supplied inputs.
+ * local:  curr_x := x3n, then every force's project() (z, u, prox state updated; read them with admmb_get_state).
+ * global: b = M x_bar + dt^2 D^T W^2 (z - u) from the current z, u, then the solve; result in ADMMB_STATE_X. */
+int admmb_debug_local_step(admmb_ctx *ctx, const double *x3n);
+int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n);
+
 /* Same step with x and v kept resident on the device (no host copies); frames >= 1 consecutive steps. */
 int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames);
 int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n);   /* either may be NULL */

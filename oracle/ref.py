@@ -59,7 +59,7 @@ def lib():
         L.ref_get_prox_state.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_get_prox_iters.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_step.argtypes = [C.c_void_p]
-        L.ref_step_dump.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.ref_step_dump.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_void_p]
         L.ref_step_timed.restype = C.c_double
         L.ref_step_timed.argtypes = [C.c_void_p, C.c_int]
         L.ref_set_omp_threads.argtypes = [C.c_int]
@@ -196,8 +196,12 @@ class RefSystem:
         xi = np.zeros((K, self.n3))
         zi = np.zeros((K, self.rows))
         ui = np.zeros((K, self.rows))
-        if self.L.ref_step_dump(self.h, xi.reshape(-1), zi.reshape(-1), ui.reshape(-1)) != 0:
+        nh = self.L.ref_get_prox_state(self.h, None)
+        pi = np.zeros((K, nh, 4))
+        if self.L.ref_step_dump(self.h, xi.reshape(-1), zi.reshape(-1), ui.reshape(-1),
+                                pi.ctypes.data_as(C.c_void_p) if nh else None) != 0:
             raise RuntimeError("reference step_dump failed")
+        self.last_prox_it = pi
         return xi, zi, ui, self.x
 
     def step_timed(self, frames):

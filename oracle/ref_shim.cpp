@@ -80,9 +80,10 @@ struct Shim {
 	std::vector<long> live_start, live_count;
 	long live_rows;
 	// dump targets (set by ref_step_dump)
-	double *dump_x, *dump_z, *dump_u;
+	double *dump_x, *dump_z, *dump_u, *dump_prox;
+	int n_hyper;
 	mutable int dump_iter;
-	Shim() : live_rows(0), dump_x(0), dump_z(0), dump_u(0), dump_iter(0) {}
+	Shim() : live_rows(0), dump_x(0), dump_z(0), dump_u(0), dump_prox(0), n_hyper(0), dump_iter(0) {}
 
 	static int rows_of(const Force *f, long n3) {
 		if (dynamic_cast<const Spring *>(f)) return 3;
@@ -133,6 +134,16 @@ void ProbeForce::project(double, const Eigen::VectorXd &Dx, Eigen::VectorXd &u, 
 	std::memcpy(owner->dump_x + (long)it * n3, Dx.data() + global_idx, sizeof(double) * n3);
 	if (owner->dump_z) owner->compact(z, owner->dump_z + (long)it * owner->live_rows);
 	if (owner->dump_u) owner->compact(u, owner->dump_u + (long)it * owner->live_rows);
+	if (owner->dump_prox) {
+		double *o = owner->dump_prox + (long)it * owner->n_hyper * 4;
+		for (size_t i = 0; i < owner->sys.forces.size(); ++i) {
+			const HyperElasticTet *t = dynamic_cast<const HyperElasticTet *>(owner->sys.forces[i].get());
+			if (!t) continue;
+			for (int j = 0; j < 3; ++j) o[j] = t->last_prox_result[j];
+			o[3] = t->solver->settings_.init_hess;
+			o += 4;
+		}
+	}
 }
 
 } // namespace
@@ -354,17 +365,22 @@ int ref_step(void *h) { return ((Shim *)h)->sys.step() ? 0 : -1; }
 
 // One unmodified step() with per-iteration dumps: x_it[it] = curr_x entering iteration it
 // (x_it[0] = x_bar), z_it/u_it[it] = compact z,u after the local step of iteration it.
+// prox_it[it] (may be NULL) = {last_prox_result[3], init_hess} of every HyperElasticTet after that local step.
 // Final x is read with ref_get_x.  Requires ref_initialize(h, 1).  Runs single-threaded.
-int ref_step_dump(void *h, double *x_it, double *z_it, double *u_it) {
+int ref_step_dump(void *h, double *x_it, double *z_it, double *u_it, double *prox_it) {
 	Shim *s = (Shim *)h;
 	if (!s->probe) return -2;
+	s->dump_prox = prox_it;
+	s->n_hyper = 0;
+	for (size_t i = 0; i < s->sys.forces.size(); ++i)
+		if (dynamic_cast<HyperElasticTet *>(s->sys.forces[i].get())) s->n_hyper++;
 #ifdef _OPENMP
 	int old = omp_get_max_threads();
 	omp_set_num_threads(1);
 #endif
 	s->dump_x = x_it; s->dump_z = z_it; s->dump_u = u_it; s->dump_iter = 0;
 	bool ok = s->sys.step();
-	s->dump_x = s->dump_z = s->dump_u = 0;
+	s->dump_x = s->dump_z = s->dump_u = s->dump_prox = 0;
 #ifdef _OPENMP
 	omp_set_num_threads(old);
 #endif

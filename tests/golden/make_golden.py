@@ -25,10 +25,24 @@ def main():
         ad = RefAdapter(sc["scene"])
         res = run_scenario(ad, sc, dump=True)
         ad.close()
+        # the reference's own sensitivity: same run from initial positions perturbed by 1e-15 (relative)
+        ad = RefAdapter(sc["scene"])
+        per = run_scenario(ad, sc, dump=True, perturb=1e-15)
+        ad.close()
+        for key in ("x_it", "z_it", "u_it", "x", "v"):
+            a, g = per[key], res[key]
+            if a.size == 0:
+                res["sens_" + key] = np.float64(0.0)
+                continue
+            flat = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
+            num = np.linalg.norm(flat[0] - flat[1], axis=1)
+            den = np.linalg.norm(flat[1], axis=1)
+            res["sens_" + key] = np.float64(np.max(np.where(den > 0, num / np.where(den > 0, den, 1.0), num)))
         scenes.save_scene(os.path.join(HERE, f"{name}.scene.npz"), sc["scene"])
         np.savez_compressed(os.path.join(HERE, f"{name}.ref.npz"), **res)
         sz = os.path.getsize(os.path.join(HERE, f"{name}.ref.npz")) / 1024
-        print(f"{name:14s} frames={sc['frames']} x_it{res['x_it'].shape} z_it{res['z_it'].shape} -> {sz:.0f} KiB")
+        print(f"{name:14s} frames={sc['frames']} x_it{res['x_it'].shape} z_it{res['z_it'].shape} -> {sz:.0f} KiB   "
+              f"self-sensitivity x_it {res['sens_x_it']:.1e} z_it {res['sens_z_it']:.1e} u_it {res['sens_u_it']:.1e} v {res['sens_v']:.1e}")
 
 
 if __name__ == "__main__":

@@ -43,6 +43,7 @@ class RefAdapter:
 
     def step_dump(self):
         xi, zi, ui, xf = self.sim.step_dump()
+        self.last_prox_it = self.sim.last_prox_it
         return xi, zi, ui, xf, self.sim.v
 
     def step(self):
@@ -103,12 +104,17 @@ class DevAdapter:
         self.sim.close()
 
 
-def run_scenario(adapter, scenario, dump=True):
-    """Runs `frames` steps; returns dict of stacked per-frame arrays."""
+def run_scenario(adapter, scenario, dump=True, perturb=None):
+    """Runs `frames` steps; returns dict of stacked per-frame arrays.  perturb = relative size of a random
+    +-perturbation of the initial positions (used to measure the reference's own sensitivity)."""
     sc = scenario["scene"]
-    if "x_after_init" in sc:
-        adapter.set_x(sc["x_after_init"])
-    out = dict(x_it=[], z_it=[], u_it=[], x=[], v=[])
+    x0 = np.asarray(sc.get("x_after_init", sc["x"]), dtype=np.float64)
+    if perturb:
+        sgn = np.random.default_rng(99).choice([-1.0, 1.0], size=x0.shape)
+        x0 = x0 * (1.0 + perturb * sgn)
+    if "x_after_init" in sc or perturb:
+        adapter.set_x(x0)
+    out = dict(x_it=[], z_it=[], u_it=[], x=[], v=[], prox_it=[])
     ev = scenario.get("events")
     for f in range(scenario["frames"]):
         if ev is not None:
@@ -118,6 +124,9 @@ def run_scenario(adapter, scenario, dump=True):
             out["x_it"].append(xi)
             out["z_it"].append(zi)
             out["u_it"].append(ui)
+            pi = getattr(adapter, "last_prox_it", None)
+            if pi is not None and pi.size:
+                out["prox_it"].append(pi)
         else:
             x, v = adapter.step()
         out["x"].append(x)
