@@ -50,6 +50,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	pcg_destroy(ctx);
 	direct_destroy(ctx);
 	for (cudaEvent_t ev : ctx->timing.ev) cudaEventDestroy(ev);
+	for (int k = 0; k < 2; ++k) if (ctx->ev_region[k]) cudaEventDestroy(ctx->ev_region[k]);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -509,6 +510,8 @@ extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
 	CHECK_READY(ctx);
 	if (admm_iters < 0 || frames < 1) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step_resident: bad arguments");
 	const bool timed = ctx->timing.on;
+	if (!ctx->ev_region[0]) { cudaEventCreate(&ctx->ev_region[0]); cudaEventCreate(&ctx->ev_region[1]); }
+	ADMMB_CUDA(ctx, cudaEventRecord(ctx->ev_region[0], ctx->stream));
 	for (int f = 0; f < frames; ++f) {
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
 		if (timed) { ctx->timing.used = 0; e0 = next_event(ctx); }
@@ -519,7 +522,18 @@ extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
 		ctx->elapsed_s += ctx->dt;
 		if (timed) { e1 = next_event(ctx); if ((rc = collect_timing(ctx, admm_iters, e0, e1))) return rc; }
 	}
+	ADMMB_CUDA(ctx, cudaEventRecord(ctx->ev_region[1], ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	float ms = 0.f;
+	ADMMB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_region[0], ctx->ev_region[1]));
+	ctx->last_region_ms = ms;
+	return ADMMB_OK;
+}
+
+extern "C" int admmb_last_region_ms(admmb_ctx *ctx, double *ms) {
+	CHECK_CTX(ctx);
+	if (!ms) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null output");
+	*ms = ctx->last_region_ms;
 	return ADMMB_OK;
 }
 

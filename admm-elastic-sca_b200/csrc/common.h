@@ -138,6 +138,8 @@ struct admmb_ctx {
 	long cg_iters_total = 0;
 	double factor_seconds = 0.0;
 	admmb::Timing timing;
+	cudaEvent_t ev_region[2] = { nullptr, nullptr }; // around the last admmb_step_resident call
+	double last_region_ms = 0.0;
 };
 
 #define ADMMB_FAIL(ctx, code, ...)                                  \

@@ -14,263 +14,37 @@
 // reference's Eigen/cppoptlib arithmetic); this translation unit is compiled with -fmad=false so that no
 // multiply-add is contracted where the reference (x86-64, no FMA) rounds twice.
 #include "common.h"
-#include "elastic_math.h"
+#include "local_bodies.h"
 
 namespace admmb {
 
-struct LocalArgs {
-	int count;
-	const int *idx;       // [nv][count]
-	const double *S;      // [nsel][count]
-	const double *w;      // [count]
-	const double *wdt2;   // [count]  dt^2 w^2
-	const double *kk;     // [count]
-	double *aux;          // [naux][count]
-	double *u, *z;        // [rows][count]
-	double *state;        // [nstate][count]
-	int *its;             // [count] or null
-	const int *active;    // moving anchors
-	const double *x;      // [n][3]
-	double *P;            // [slots][3], already offset to this batch's first slot
-	double p0, p1, p2;
-	int max_iterations, flag;
-	const int *shape_kind;
-	const double *shape_params;
-	int nshapes;
-};
-
 #define LOCAL_THREADS 128
 
-// ---- tets -------------------------------------------------------------------------------------------
 template <int KIND, int MH>
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_tets(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-
-	double B[12], Dx[9], u[9], q[9], z[9];
-#pragma unroll
-	for (int k = 0; k < 12; ++k) B[k] = a.S[(size_t)k * n + e];
-	{
-		double xs[4][3];
-#pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const int id = a.idx[(size_t)c * n + e];
-#pragma unroll
-			for (int j = 0; j < 3; ++j) xs[c][j] = a.x[3 * (size_t)id + j];
-		}
-		// row 3r+j of D_i x = sum_c B(c,r) x_c[j]   (TetForce.cpp:67-75)
-#pragma unroll
-		for (int r = 0; r < 3; ++r)
-#pragma unroll
-			for (int j = 0; j < 3; ++j)
-				Dx[3 * r + j] = ((B[0 * 3 + r] * xs[0][j] + B[1 * 3 + r] * xs[1][j]) + B[2 * 3 + r] * xs[2][j]) + B[3 * 3 + r] * xs[3][j];
-	}
-#pragma unroll
-	for (int k = 0; k < 9; ++k) { u[k] = a.u[(size_t)k * n + e]; q[k] = Dx[k] + u[k]; }
-
-	if (KIND == ADMMB_TET_LINEAR_STRAIN) {
-		arap_tet_z(q, a.kk[e], a.w[e], z);
-	} else if (KIND == ADMMB_TET_VOLUME) {
-		volume_tet_z(q, a.kk[e], a.w[e], a.p1, a.p2, z);
-	} else {
-		double st[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) st[k] = a.state[(size_t)k * n + e];
-		int its;
-		if (KIND == ADMMB_TET_NEOHOOKEAN) its = hyperelastic_tet_z<NHModel, MH>(q, a.p0, a.p1, a.kk[e], a.max_iterations, st, z);
-		else its = hyperelastic_tet_z<StVKModel, MH>(q, a.p0, a.p1, a.kk[e], a.max_iterations, st, z);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) a.state[(size_t)k * n + e] = st[k];
-		if (a.its) a.its[e] = its;
-	}
-
-	double zu[9];
-#pragma unroll
-	for (int k = 0; k < 9; ++k) {
-		const double un = u[k] + (Dx[k] - z[k]); // ui += (Dix - zi)
-		a.u[(size_t)k * n + e] = un;
-		a.z[(size_t)k * n + e] = z[k];
-		zu[k] = z[k] - un;                       // curr_z - curr_u
-	}
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 12;
-#pragma unroll
-	for (int v = 0; v < 4; ++v)
-#pragma unroll
-		for (int j = 0; j < 3; ++j)
-			P[3 * v + j] = c * ((B[v * 3 + 0] * zu[j] + B[v * 3 + 1] * zu[3 + j]) + B[v * 3 + 2] * zu[6 + j]);
+	if (e < a.count) local_tet<KIND, MH>(a, e);
 }
-
-// ---- triangles --------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_tris(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-	double B[6], Dx[6], u[6], q[6], z[6]; // B(j,c) at [j*2+c]
-#pragma unroll
-	for (int k = 0; k < 6; ++k) B[k] = a.S[(size_t)k * n + e];
-	{
-		double xs[3][3];
-#pragma unroll
-		for (int c = 0; c < 3; ++c) {
-			const int id = a.idx[(size_t)c * n + e];
-#pragma unroll
-			for (int j = 0; j < 3; ++j) xs[c][j] = a.x[3 * (size_t)id + j];
-		}
-		// rows i and 3+i: sum_j B(j,0) x_j[i], sum_j B(j,1) x_j[i]   (TriangleForce.cpp:65-76)
-#pragma unroll
-		for (int c = 0; c < 2; ++c)
-#pragma unroll
-			for (int i = 0; i < 3; ++i)
-				Dx[3 * c + i] = (B[0 * 2 + c] * xs[0][i] + B[1 * 2 + c] * xs[1][i]) + B[2 * 2 + c] * xs[2][i];
-	}
-#pragma unroll
-	for (int k = 0; k < 6; ++k) { u[k] = a.u[(size_t)k * n + e]; q[k] = Dx[k] + u[k]; }
-
-	if (KIND == ADMMB_TRI_LIMITED_STRAIN) tri_strain_z(q, a.kk[e], a.w[e], a.p1, a.p2, a.flag != 0, z);
-	else if (KIND == ADMMB_TRI_AREA) tri_area_z(q, a.kk[e], a.w[e], a.p1, a.p2, a.flag, z);
-	else {
-		double ih = a.state[e];
-		fung_tri_z(q, a.p0, &ih, z);
-		a.state[e] = ih;
-	}
-	double zu[6];
-#pragma unroll
-	for (int k = 0; k < 6; ++k) {
-		const double un = u[k] + (Dx[k] - z[k]);
-		a.u[(size_t)k * n + e] = un;
-		a.z[(size_t)k * n + e] = z[k];
-		zu[k] = z[k] - un;
-	}
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 9;
-#pragma unroll
-	for (int v = 0; v < 3; ++v)
-#pragma unroll
-		for (int j = 0; j < 3; ++j) P[3 * v + j] = c * (B[v * 2 + 0] * zu[j] + B[v * 2 + 1] * zu[3 + j]);
+	if (e < a.count) local_tri<KIND>(a, e);
 }
-
-// ---- springs ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_springs(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-	const int i0 = a.idx[e], i1 = a.idx[(size_t)n + e];
-	double Dx[3], u[3], q[3], z[3];
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		Dx[j] = a.x[3 * (size_t)i0 + j] - a.x[3 * (size_t)i1 + j]; // rows: +1 at idx0, -1 at idx1 (Force.cpp:44-47)
-		u[j] = a.u[(size_t)j * n + e];
-		q[j] = Dx[j] + u[j];
-	}
-	spring_z(q, a.kk[e], a.w[e], a.aux[e], z);
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 6;
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		const double un = u[j] + (Dx[j] - z[j]);
-		a.u[(size_t)j * n + e] = un;
-		a.z[(size_t)j * n + e] = z[j];
-		const double f = c * (z[j] - un);
-		P[j] = f;
-		P[3 + j] = -f;
-	}
+	if (e < a.count) local_spring(a, e);
 }
-
-// ---- bending hinges ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_bends(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-	double xs[4][3];
-#pragma unroll
-	for (int c = 0; c < 4; ++c) {
-		const int id = a.idx[(size_t)c * n + e];
-#pragma unroll
-		for (int j = 0; j < 3; ++j) xs[c][j] = a.x[3 * (size_t)id + j];
-	}
-	double Dx[9], u[9], q[9], z[9], al[4];
-#pragma unroll
-	for (int j = 0; j < 3; ++j) { // rows (x0-x2), (x3-x2), (x1-x2)   BendForce.cpp:89-128
-		Dx[j] = xs[0][j] - xs[2][j];
-		Dx[3 + j] = xs[3][j] - xs[2][j];
-		Dx[6 + j] = xs[1][j] - xs[2][j];
-	}
-#pragma unroll
-	for (int k = 0; k < 9; ++k) { u[k] = a.u[(size_t)k * n + e]; q[k] = Dx[k] + u[k]; }
-#pragma unroll
-	for (int k = 0; k < 4; ++k) al[k] = a.aux[(size_t)k * n + e];
-	bend_z(q, a.kk[e], a.w[e], al, z);
-	double zu[9];
-#pragma unroll
-	for (int k = 0; k < 9; ++k) {
-		const double un = u[k] + (Dx[k] - z[k]);
-		a.u[(size_t)k * n + e] = un;
-		a.z[(size_t)k * n + e] = z[k];
-		zu[k] = z[k] - un;
-	}
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 12;
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		P[0 * 3 + j] = c * zu[j];                                  // node idx0: +row0
-		P[1 * 3 + j] = c * zu[6 + j];                              // node idx1: +row2
-		P[2 * 3 + j] = c * ((-zu[j] - zu[3 + j]) - zu[6 + j]);     // node idx2: -row0 -row1 -row2
-		P[3 * 3 + j] = c * zu[3 + j];                              // node idx3: +row1
-	}
+	if (e < a.count) local_bend(a, e);
 }
-
-// ---- anchors (StaticAnchor / MovingAnchor) ---------------------------------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_anchors(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-	const int id = a.idx[e];
-	const bool act = a.active ? (a.active[e] != 0) : true;
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 3;
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		const double Dx = a.x[3 * (size_t)id + j];
-		const double u = a.u[(size_t)j * n + e];
-		double z;
-		if (act) {
-			z = a.aux[(size_t)j * n + e];       // zi = pos (AnchorForce.cpp:46-55, :76-77)
-		} else {
-			z = Dx + u;                          // zi = Dix + ui; point->pos = Dx  (AnchorForce.cpp:79-83)
-			a.aux[(size_t)j * n + e] = Dx;
-		}
-		const double un = u + (Dx - z);
-		a.u[(size_t)j * n + e] = un;
-		a.z[(size_t)j * n + e] = z;
-		P[j] = c * (z - un);
-	}
+	if (e < a.count) local_anchor(a, e);
 }
-
-// ---- collision (one "force" spanning all nodes; one thread per node) --------------------------------
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_collision(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= a.count) return;
-	const int n = a.count;
-	double Dx[3], u[3], p[3];
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		Dx[j] = a.x[3 * (size_t)e + j];
-		u[j] = a.u[(size_t)j * n + e];
-		p[j] = Dx[j] + u[j];
-	}
-	collide_point(p, a.shape_params, a.shape_kind, a.nshapes);
-	const double c = a.wdt2[e];
-	double *P = a.P + (size_t)e * 3;
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-		const double un = u[j] + (Dx[j] - p[j]);
-		a.u[(size_t)j * n + e] = un;
-		a.z[(size_t)j * n + e] = p[j];
-		P[j] = c * (p[j] - un);
-	}
+	if (e < a.count) local_collision(a, e);
 }
 
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {

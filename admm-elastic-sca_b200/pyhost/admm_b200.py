@@ -26,7 +26,7 @@ EXPORTS = [
     "admmb_step_dump", "admmb_debug_local_step", "admmb_debug_global_step", "admmb_step_resident", "admmb_upload_xv", "admmb_download_xv", "admmb_update_anchor_targets",
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
-    "admmb_timing_read",
+    "admmb_timing_read", "admmb_last_region_ms",
 ]
 
 
@@ -83,6 +83,7 @@ def lib():
     L.admmb_get_info.argtypes = [vp, C.POINTER(Info)]
     L.admmb_timing_enable.argtypes = [vp, C.c_int]
     L.admmb_timing_read.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
+    L.admmb_last_region_ms.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -282,6 +283,11 @@ class System:
         i = Info()
         self._ck(self.L.admmb_get_info(self.h, C.byref(i)))
         return {f: getattr(i, f) for f, _ in Info._fields_}
+
+    def last_region_ms(self):
+        ms = C.c_double(0.0)
+        self._ck(self.L.admmb_last_region_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def timing(self, on):
         self._ck(self.L.admmb_timing_enable(self.h, 1 if on else 0))

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM iterations per second on the synthetic tetrahedralised cube (BASELINE.json configs[4]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--cube 55] [--impl reference]
+
+One "step" is one System::step() frame = `admm_iters` (10) ADMM iterations of the hot path (local step for
+every force + global step) on the N^3 Kuhn cube with NeoHookean tets (mu = lambda = 1e5, max_iterations 5,
+density-weighted mass 1000, gravity, dt 0.04, x1.3 stretch excitation) -- SURVEY.md 8(d) input 5.
+  value   whole-job ADMM iterations/s with x, v resident in HBM (admmb_step_resident), CUDA events on the
+          library's stream, max over ranks;
+  e2e     the same through the reference-facing call admmb_step() with HOST x/v buffers (pinned staging,
+          H2D + D2H inside the timed region), host wall clock;
+  N > 1   scene ensemble: every rank steps its own copy of the scene on its own GPU, no data-path collective
+          ("scaling": "weak"); torch.distributed (NCCL) only carries the barrier and the max-over-ranks.
+  --impl reference   the UNMODIFIED reference (oracle/_ref, Eigen + OpenMP on the host cores) on a bounded sample
+          of the same workload (a smaller cube), scaled to the metric's unit by tet count (see "sample").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "admm-elastic-sca_b200", "pyhost"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "admm_iterations_per_s_cube_1M_tets"
+UNIT = "ADMM iterations/s"
+ADMM_ITERS = 10
+FULL_TETS = 998250  # N = 55
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(N):
+    import scenes
+    return scenes.cube_scene(N, kind=scenes.TET_NH, mu=1e5, lam=1e5, maxit=5, mass=1000.0, dt=0.04, iters=ADMM_ITERS, stretch=1.3)
+
+
+def run_reference(args, rank, world):
+    """Times the unmodified reference on the host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libadmm_ref.so missing (build it where /root/reference exists)"}))
+        return
+    N = args.ref_cube
+    sc = make_scene(N)
+    ntets = sc["batches"][0]["idx"].shape[0]
+    cores = os.cpu_count() or 1
+    ref.lib().ref_set_omp_threads(cores)
+    t0 = time.perf_counter()
+    sim = ref.RefSystem(sc, probe=False)
+    t_init = time.perf_counter() - t0
+    sim.set_x(sc["x_after_init"])
+    for _ in range(args.warmup):
+        sim.step()
+    sec = sim.step_timed(args.steps)
+    stats = sim.stats()
+    sim.close()
+    its = args.steps * ADMM_ITERS / sec
+    value = its * ntets / FULL_TETS  # scaled by tet count to the 1M-tet unit (generous: the reference's cost grows superlinearly)
+    sample = (f"cube N={N} ({ntets} tets) stepped {args.steps} frames x {ADMM_ITERS} iterations = {its:.2f} it/s measured, "
+              f"scaled x{ntets}/{FULL_TETS} to the 1M-tet unit; initialize() {t_init:.1f} s not included; L nnz {stats['L_nnz']}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cube N={args.cube} NeoHookean, {ADMM_ITERS} ADMM iterations per step (reference timed on N={N})"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(N):
+    from oracle import ref
+    if not ref.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    sc = make_scene(N)
+    ntets = sc["batches"][0]["idx"].shape[0]
+    cores = os.cpu_count() or 1
+    ref.lib().ref_set_omp_threads(cores)
+    t0 = time.perf_counter()
+    sim = ref.RefSystem(sc, probe=False)
+    t_init = time.perf_counter() - t0
+    sim.set_x(sc["x_after_init"])
+    sim.step()
+    frames = 8
+    sec = sim.step_timed(frames)
+    sim.close()
+    its = frames * ADMM_ITERS / sec
+    return {"value": its * ntets / FULL_TETS, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"unmodified reference (Eigen + OpenMP, {cores} threads) on cube N={N} ({ntets} tets): {its:.2f} it/s over {frames} frames, "
+                      f"scaled x{ntets}/{FULL_TETS}; initialize() {t_init:.1f} s excluded"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cube", type=int, default=55, help="cube resolution N (N=55: 998,250 tets)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-cube", type=int, default=30, help="cube resolution of the reference arm's bounded sample")
+    ap.add_argument("--cpu-cube", type=int, default=20, help="cube resolution of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="direct", choices=["direct", "pcg"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import admm_b200
+    sc = make_scene(args.cube)
+    ntets = sc["batches"][0]["idx"].shape[0]
+    nverts = sc["x"].shape[0]
+    t0 = time.perf_counter()
+    sim = admm_b200.System(sc, device=local_rank, solver=admm_b200.SOLVER_DIRECT if args.solver == "direct" else admm_b200.SOLVER_PCG,
+                           cg_tol=1e-10)
+    t_setup = time.perf_counter() - t0
+    info0 = sim.info()
+    sim.set_x(sc["x_after_init"])
+    sim.upload()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident path: `value` -----------------------------------------------------------------------------
+    sim.step_resident(frames=args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = sim.info()["launches_total"]
+    sim.step_resident(frames=args.steps)      # the timed region: K frames, CUDA events on the library's stream
+    ms_region = sim.last_region_ms()
+    l1 = sim.info()["launches_total"]
+    barrier()
+    clocks = sampler.stop()
+    # second pass with per-phase events (not part of `value`): local / rhs / solve split
+    sim.timing(True)
+    sim.timing_read(reset=True)
+    sim.step_resident(frames=max(2, args.steps // 2))
+    phases = sim.timing_read(reset=True)
+    sim.timing(False)
+
+    # ---- end to end through admmb_step with host buffers: `e2e` ---------------------------------------------------
+    sim.download()
+    for _ in range(2):
+        sim.step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.step()
+    torch.cuda.synchronize()
+    sec_e2e = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([ms_region, sec_e2e * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_region_max, ms_e2e_max = float(t[0]), float(t[1])
+    total_iters = world * args.steps * ADMM_ITERS
+    value = total_iters / (ms_region_max * 1e-3)
+    e2e_value = total_iters / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        hbm_peak = (pk or {}).get("hbm_gbs", 6650.0)
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (copy, of measured)" if pk else "fallback 6650 GB/s (B200_PROFILING.md, of fallback)"
+        iters = max(phases["iters"], 1)
+        solve_ms = phases["solve_ms"] / iters
+        local_ms = phases["local_ms"] / iters
+        rhs_ms = phases["rhs_ms"] / iters
+        # dominant kernel of the global step: k_solve_level streams the packed factor once forward and once backward
+        solve_bytes = info0["factor_bytes"] + 9 * nverts * 8 * 3  # factor tiles + b, y, x vectors read/written
+        solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+        # local step: algorithmic bytes per tet-iteration: idx 16 + x gather 96 + B 96 + u r/w 144 + z w 72
+        # + state r/w 64 + weights 24 + P w 96 = 608 B
+        local_bytes = 608.0 * ntets
+        local_gbs = local_bytes / (local_ms * 1e-3) / 1e9 if local_ms > 0 else 0.0
+        dominant = "k_solve_level" if solve_ms >= local_ms else "k_local_tets<NeoHookean>"
+        if dominant == "k_solve_level":
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": solve_gbs / hbm_peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "note": f"{info0['n_levels']} levels x 2 launches per solve; bytes = packed factor ({info0['factor_bytes']} B, both copies) + vectors"}
+        else:
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": local_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": local_gbs / hbm_peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "FP64-latency bound kernel (SVD + L-BFGS per tet); HBM fraction reported because the schema asks for it"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_region_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cube N={args.cube} ({ntets} tets, {nverts} nodes) NeoHookean mu=lambda=1e5 max_iterations=5, "
+                                   f"{ADMM_ITERS} ADMM iterations per step (System::step), dt 0.04, x1.3 stretch; solver={args.solver}",
+                       "parallelism": f"ensemble x{world} (one scene per GPU, no collective)" if world > 1 else "single GPU",
+                       "l2": "working set (factor %.2f GB + force arrays %.2f GB) exceeds the 126 MB L2, no flush needed" % (
+                           info0["factor_bytes"] / 1e9, 608.0 * ntets / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 3 * nverts * 8, "d2h_bytes_per_step": 2 * 3 * nverts * 8,
+                    "ms_per_step": ms_e2e_max / args.steps},
+            "gpu_launches": int(l1 - l0),
+            "clocks": clocks,
+            "roofline": roof,
+            "phases_ms_per_iteration": {"local": local_ms, "rhs": rhs_ms, "solve": solve_ms,
+                                        "local_GBps_algorithmic": local_gbs, "solve_GBps": solve_gbs},
+            "setup": {"seconds": t_setup, "factor_seconds": info0["factor_seconds"], "nnz_L": info0["nnz_L"],
+                      "supernodes": info0["n_supernodes"], "levels": info0["n_levels"], "factor_bytes": info0["factor_bytes"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args.cpu_cube)
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

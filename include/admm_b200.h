@@ -163,6 +163,8 @@ int admmb_get_info(admmb_ctx *ctx, admmb_info *out);
  * accumulated since the last reset; iters = ADMM iterations accumulated. */
 int admmb_timing_enable(admmb_ctx *ctx, int on);
 int admmb_timing_read(admmb_ctx *ctx, double *ms4, long *iters, int reset);
+/* Device time (CUDA events on the context's stream) of the whole last admmb_step_resident call, all frames. */
+int admmb_last_region_ms(admmb_ctx *ctx, double *ms);
 
 #ifdef __cplusplus
 }
