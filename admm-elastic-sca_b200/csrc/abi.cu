@@ -29,11 +29,14 @@ extern "C" int admmb_create(int device, admmb_ctx **out) {
 	if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ADMMB_E_CUDA; }
 	admmb_ctx *ctx = new admmb_ctx();
 	ctx->device = device;
+	if (getenv("ADMMB_NO_GRAPH")) ctx->use_graph = false;
 	e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ADMMB_E_CUDA; }
 	*out = ctx;
 	return ADMMB_OK;
 }
+
+static void drop_iteration_graph(admmb_ctx *ctx);
 
 static void free_batch(Batch &b) {
 	b.d_idx.free(); b.d_S.free(); b.d_w.free(); b.d_wdt2.free(); b.d_kk.free(); b.d_aux.free(); b.d_u.free(); b.d_z.free();
@@ -47,6 +50,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	for (Batch &b : ctx->batches) free_batch(b);
 	ctx->d_x.free(); ctx->d_v.free(); ctx->d_xbar.free(); ctx->d_Mxbar.free(); ctx->d_currx.free(); ctx->d_b.free(); ctx->d_m.free();
 	ctx->d_io.free(); ctx->d_node_perm.free(); ctx->d_P.free(); ctx->d_vert_ptr.free(); ctx->d_vert_slots.free();
+	drop_iteration_graph(ctx);
 	pcg_destroy(ctx);
 	direct_destroy(ctx);
 	for (cudaEvent_t ev : ctx->timing.ev) cudaEventDestroy(ev);
@@ -353,9 +357,46 @@ static cudaEvent_t next_event(admmb_ctx *ctx) {
 
 struct DumpTarget { double *x_it, *z_it, *u_it; };
 
+static void drop_iteration_graph(admmb_ctx *ctx) {
+	if (ctx->iter_graph_exec) cudaGraphExecDestroy(ctx->iter_graph_exec);
+	if (ctx->iter_graph) cudaGraphDestroy(ctx->iter_graph);
+	ctx->iter_graph_exec = nullptr;
+	ctx->iter_graph = nullptr;
+}
+
+// One ADMM iteration (System.cpp:51-66): local step of every batch, right-hand side, solve.
+static int enqueue_iteration(admmb_ctx *ctx) {
+	const double dt2 = ctx->dt * ctx->dt;
+	for (Batch &b : ctx->batches) {
+		int rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
+		if (rc) return rc;
+	}
+	int rc = launch_rhs(ctx);
+	if (rc) return rc;
+	return (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_solve(ctx) : direct_solve(ctx);
+}
+
 static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump = nullptr) {
 	const bool timed = ctx->timing.on && !dump;
 	const double dt2 = ctx->dt * ctx->dt;
+	// Fast path: the iteration is a fixed sequence of ~35 small launches with fixed arguments, so it is captured
+	// once into a CUDA graph and replayed (the PCG solve polls a convergence flag from the host and cannot be).
+	if (!timed && !dump && ctx->use_graph && ctx->solver == ADMMB_SOLVER_DIRECT && admm_iters > 0) {
+		if (!ctx->iter_graph_exec) {
+			const long before = ctx->launches;
+			ADMMB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+			int rc = enqueue_iteration(ctx);
+			cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->iter_graph);
+			if (rc) { drop_iteration_graph(ctx); return rc; }
+			ADMMB_CUDA(ctx, e);
+			ADMMB_CUDA(ctx, cudaGraphInstantiate(&ctx->iter_graph_exec, ctx->iter_graph, 0));
+			ctx->iter_graph_launches = ctx->launches - before;
+			ctx->launches = before;
+		}
+		for (int it = 0; it < admm_iters; ++it) ADMMB_CUDA(ctx, cudaGraphLaunch(ctx->iter_graph_exec, ctx->stream));
+		ctx->launches += ctx->iter_graph_launches * admm_iters;
+		return ADMMB_OK;
+	}
 	for (int it = 0; it < admm_iters; ++it) {
 		if (timed) next_event(ctx);
 		if (dump && dump->x_it) {
@@ -610,6 +651,7 @@ extern "C" int admmb_get_batch_weights(admmb_ctx *ctx, int batch, double *weight
 
 extern "C" int admmb_recompute_weights(admmb_ctx *ctx) {
 	CHECK_READY(ctx);
+	drop_iteration_graph(ctx); // weight arrays and the factor are re-allocated
 	for (Batch &b : ctx->batches) {
 		int rc = upload_batch_weights(ctx, b);
 		if (rc) return rc;

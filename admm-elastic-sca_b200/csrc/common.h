@@ -138,6 +138,10 @@ struct admmb_ctx {
 	long cg_iters_total = 0;
 	double factor_seconds = 0.0;
 	admmb::Timing timing;
+	bool use_graph = true;
+	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)
+	cudaGraphExec_t iter_graph_exec = nullptr;
+	long iter_graph_launches = 0;
 	cudaEvent_t ev_region[2] = { nullptr, nullptr }; // around the last admmb_step_resident call
 	double last_region_ms = 0.0;
 };

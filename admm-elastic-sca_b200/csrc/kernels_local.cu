@@ -18,12 +18,27 @@
 
 namespace admmb {
 
+#ifndef LOCAL_THREADS
 #define LOCAL_THREADS 128
+#endif
+#ifndef HYPER_THREADS
+#define HYPER_THREADS 256
+#endif
+#ifndef HYPER_MIN_BLOCKS
+#define HYPER_MIN_BLOCKS 3
+#endif
 
 template <int KIND, int MH>
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_tets(const LocalArgs a) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e < a.count) local_tet<KIND, MH>(a, e);
+}
+// hyperelastic tets: U, V of the SVD are parked in shared memory while the optimiser runs (local_bodies.h)
+template <class Model, int MH>
+__global__ void __launch_bounds__(HYPER_THREADS, HYPER_MIN_BLOCKS) k_local_tets_hyper(const LocalArgs a) {
+	__shared__ double park[18 * HYPER_THREADS];
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < a.count) local_tet_hyper<Model, MH>(a, e, park + threadIdx.x, HYPER_THREADS);
 }
 template <int KIND>
 __global__ void __launch_bounds__(LOCAL_THREADS) k_local_tris(const LocalArgs a) {
@@ -66,14 +81,18 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 		switch (b.kind) {
 		case ADMMB_TET_LINEAR_STRAIN: k_local_tets<ADMMB_TET_LINEAR_STRAIN, 1><<<grid, LOCAL_THREADS, 0, s>>>(a); break;
 		case ADMMB_TET_VOLUME: k_local_tets<ADMMB_TET_VOLUME, 1><<<grid, LOCAL_THREADS, 0, s>>>(a); break;
-		case ADMMB_TET_NEOHOOKEAN:
-			if (b.max_iterations <= 5) k_local_tets<ADMMB_TET_NEOHOOKEAN, 5><<<grid, LOCAL_THREADS, 0, s>>>(a);
-			else k_local_tets<ADMMB_TET_NEOHOOKEAN, 10><<<grid, LOCAL_THREADS, 0, s>>>(a);
+		case ADMMB_TET_NEOHOOKEAN: {
+			const int g = (b.count + HYPER_THREADS - 1) / HYPER_THREADS;
+			if (b.max_iterations <= 5) k_local_tets_hyper<NHModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
+			else k_local_tets_hyper<NHModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
 			break;
-		case ADMMB_TET_STVK:
-			if (b.max_iterations <= 5) k_local_tets<ADMMB_TET_STVK, 5><<<grid, LOCAL_THREADS, 0, s>>>(a);
-			else k_local_tets<ADMMB_TET_STVK, 10><<<grid, LOCAL_THREADS, 0, s>>>(a);
+		}
+		case ADMMB_TET_STVK: {
+			const int g = (b.count + HYPER_THREADS - 1) / HYPER_THREADS;
+			if (b.max_iterations <= 5) k_local_tets_hyper<StVKModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
+			else k_local_tets_hyper<StVKModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
 			break;
+		}
 		}
 		break;
 	case BT_TRIS:

@@ -29,47 +29,29 @@ struct LocalArgs {
 };
 
 // ---- tets -------------------------------------------------------------------------------------------
-template <int KIND, int MH>
-ADMMB_HD void local_tet(const LocalArgs &a, const int e) {
+// B(c,r) of force e and row 3r+j of D_i x = sum_c B(c,r) x_c[j] (TetForce.cpp:67-75), corners in ascending node
+// order so that the left-to-right sum rounds like Eigen's column-major sparse product (rest_state.cpp).
+ADMMB_HD void tet_load_Dx(const LocalArgs &a, const int e, double *B, double *Dx) {
 	const int n = a.count;
-
-	double B[12], Dx[9], u[9], q[9], z[9];
 #pragma unroll
 	for (int k = 0; k < 12; ++k) B[k] = a.S[(size_t)k * n + e];
-	{
-		double xs[4][3];
+	double xs[4][3];
 #pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const int id = a.idx[(size_t)c * n + e];
+	for (int c = 0; c < 4; ++c) {
+		const int id = a.idx[(size_t)c * n + e];
 #pragma unroll
-			for (int j = 0; j < 3; ++j) xs[c][j] = a.x[3 * (size_t)id + j];
-		}
-		// row 3r+j of D_i x = sum_c B(c,r) x_c[j]   (TetForce.cpp:67-75)
-#pragma unroll
-		for (int r = 0; r < 3; ++r)
-#pragma unroll
-			for (int j = 0; j < 3; ++j)
-				Dx[3 * r + j] = ((B[0 * 3 + r] * xs[0][j] + B[1 * 3 + r] * xs[1][j]) + B[2 * 3 + r] * xs[2][j]) + B[3 * 3 + r] * xs[3][j];
+		for (int j = 0; j < 3; ++j) xs[c][j] = a.x[3 * (size_t)id + j];
 	}
 #pragma unroll
-	for (int k = 0; k < 9; ++k) { u[k] = a.u[(size_t)k * n + e]; q[k] = Dx[k] + u[k]; }
-
-	if (KIND == ADMMB_TET_LINEAR_STRAIN) {
-		arap_tet_z(q, a.kk[e], a.w[e], z);
-	} else if (KIND == ADMMB_TET_VOLUME) {
-		volume_tet_z(q, a.kk[e], a.w[e], a.p1, a.p2, z);
-	} else {
-		double st[4];
+	for (int r = 0; r < 3; ++r)
 #pragma unroll
-		for (int k = 0; k < 4; ++k) st[k] = a.state[(size_t)k * n + e];
-		int its;
-		if (KIND == ADMMB_TET_NEOHOOKEAN) its = hyperelastic_tet_z<NHModel, MH>(q, a.p0, a.p1, a.kk[e], a.max_iterations, st, z);
-		else its = hyperelastic_tet_z<StVKModel, MH>(q, a.p0, a.p1, a.kk[e], a.max_iterations, st, z);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) a.state[(size_t)k * n + e] = st[k];
-		if (a.its) a.its[e] = its;
-	}
+		for (int j = 0; j < 3; ++j)
+			Dx[3 * r + j] = ((B[0 * 3 + r] * xs[0][j] + B[1 * 3 + r] * xs[1][j]) + B[2 * 3 + r] * xs[2][j]) + B[3 * 3 + r] * xs[3][j];
+}
 
+// u += D_i x - z, store u and z, and this force's share of the right-hand side dt^2 D_i^T W_i^2 (z - u).
+ADMMB_HD void tet_finish(const LocalArgs &a, const int e, const double *B, const double *Dx, const double *u, const double *z) {
+	const int n = a.count;
 	double zu[9];
 #pragma unroll
 	for (int k = 0; k < 9; ++k) {
@@ -85,6 +67,62 @@ ADMMB_HD void local_tet(const LocalArgs &a, const int e) {
 #pragma unroll
 		for (int j = 0; j < 3; ++j)
 			P[3 * v + j] = c * ((B[v * 3 + 0] * zu[j] + B[v * 3 + 1] * zu[3 + j]) + B[v * 3 + 2] * zu[6 + j]);
+}
+
+// LinearTetStrain / TetVolume: closed-form projection, everything stays in registers.
+template <int KIND, int MH>
+ADMMB_HD void local_tet(const LocalArgs &a, const int e) {
+	const int n = a.count;
+	double B[12], Dx[9], u[9], q[9], z[9];
+	tet_load_Dx(a, e, B, Dx);
+#pragma unroll
+	for (int k = 0; k < 9; ++k) { u[k] = a.u[(size_t)k * n + e]; q[k] = Dx[k] + u[k]; }
+	if (KIND == ADMMB_TET_LINEAR_STRAIN) arap_tet_z(q, a.kk[e], a.w[e], z);
+	else volume_tet_z(q, a.kk[e], a.w[e], a.p1, a.p2, z);
+	tet_finish(a, e, B, Dx, u, z);
+}
+
+// HyperElasticTet (TetForce.cpp:320-364).  The optimiser on the three singular values is where the time goes
+// (in steady state the reference's line search burns its full 20 + 2 evaluations per tet), and it needs few live
+// values: Sigma_0, the iterate, the L-BFGS history.  Everything else is kept OUT of registers while it runs --
+// U and V are parked in `park` (shared memory on the device: park[k * ps], k < 18), and D_i x, u and B are simply
+// re-read / re-formed afterwards (bit-identical: same operations on the same data) -- which takes the kernel
+// from 168 to ~100 registers and doubles the resident warps that hide the FP64 latency.
+template <class Model, int MH>
+ADMMB_HD void local_tet_hyper(const LocalArgs &a, const int e, double *park, const int ps) {
+	const int n = a.count;
+	ProxParams P;
+	P.mu = a.p0; P.lambda = a.p1; P.k = a.kk[e];
+	{
+		double B[12], q[9], U[9], V[9];
+		tet_load_Dx(a, e, B, q);
+#pragma unroll
+		for (int k = 0; k < 9; ++k) q[k] = q[k] + a.u[(size_t)k * n + e];
+		oriented_svd3(q, U, P.s0, V);
+#pragma unroll
+		for (int k = 0; k < 9; ++k) { park[k * ps] = U[k]; park[(9 + k) * ps] = V[k]; }
+	}
+	double x2[3] = { a.state[e], a.state[(size_t)n + e], a.state[2 * (size_t)n + e] };
+	double ih = a.state[3 * (size_t)n + e];
+	// initial guess needs positive entries; collapsed-node test case (TetForce.cpp:339-347)
+	if (x2[2] < 0.0) { x2[2] *= -1.0; }
+	else if (fabs(x2[0]) < 1.e-3 && fabs(x2[1]) < 1.e-3 && fabs(x2[2]) < 1.e-3) { x2[0] = 1.e-3; x2[1] = 1.e-3; x2[2] = 1.e-3; }
+	const int its = lbfgs_minimize<Model, ProxParams, 3, MH>(P, x2, a.max_iterations, 1e-8, ih);
+	a.state[e] = x2[0]; a.state[(size_t)n + e] = x2[1]; a.state[2 * (size_t)n + e] = x2[2]; a.state[3 * (size_t)n + e] = ih;
+	if (a.its) a.its[e] = its;
+
+	double z[9];
+	{
+		double U[9], V[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) { U[k] = park[k * ps]; V[k] = park[(9 + k) * ps]; }
+		usvt3(U, x2, V, z);
+	}
+	double B[12], Dx[9], u[9];
+	tet_load_Dx(a, e, B, Dx);
+#pragma unroll
+	for (int k = 0; k < 9; ++k) u[k] = a.u[(size_t)k * n + e];
+	tet_finish(a, e, B, Dx, u, z);
 }
 
 // ---- triangles --------------------------------------------------------------------------------------

@@ -67,8 +67,8 @@ extern "C" int hc_batch_local(int type, int kind, int n, const double *x_rest, i
 		case BT_TETS:
 			if (kind == ADMMB_TET_LINEAR_STRAIN) local_tet<ADMMB_TET_LINEAR_STRAIN, 1>(a, e);
 			else if (kind == ADMMB_TET_VOLUME) local_tet<ADMMB_TET_VOLUME, 1>(a, e);
-			else if (kind == ADMMB_TET_NEOHOOKEAN) { if (maxit <= 5) local_tet<ADMMB_TET_NEOHOOKEAN, 5>(a, e); else local_tet<ADMMB_TET_NEOHOOKEAN, 10>(a, e); }
-			else { if (maxit <= 5) local_tet<ADMMB_TET_STVK, 5>(a, e); else local_tet<ADMMB_TET_STVK, 10>(a, e); }
+			else if (kind == ADMMB_TET_NEOHOOKEAN) { double park[18]; if (maxit <= 5) local_tet_hyper<NHModel, 5>(a, e, park, 1); else local_tet_hyper<NHModel, 10>(a, e, park, 1); }
+			else { double park[18]; if (maxit <= 5) local_tet_hyper<StVKModel, 5>(a, e, park, 1); else local_tet_hyper<StVKModel, 10>(a, e, park, 1); }
 			break;
 		case BT_TRIS:
 			if (kind == ADMMB_TRI_LIMITED_STRAIN) local_tri<ADMMB_TRI_LIMITED_STRAIN>(a, e);
