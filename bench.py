@@ -223,11 +223,9 @@ def main():
     sec_e2e = time.perf_counter() - t0
     barrier()
 
-    t = torch.tensor([ms_region, sec_e2e * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_region_max, ms_e2e_max = float(t[0]), float(t[1])
-    total_iters = world * args.steps * ADMM_ITERS
+    import ensemble  # whole-job figures: MAX over ranks of the timed region, SUM over ranks of the units
+    ms_region_max, total_iters = ensemble.reduce_job(ms_region, args.steps * ADMM_ITERS)
+    ms_e2e_max, _ = ensemble.reduce_job(sec_e2e * 1e3, args.steps * ADMM_ITERS)
     value = total_iters / (ms_region_max * 1e-3)
     e2e_value = total_iters / (ms_e2e_max * 1e-3)
 
