@@ -141,6 +141,7 @@ struct admmb_ctx {
 	bool use_graph = true;
 	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)
 	cudaGraphExec_t iter_graph_exec = nullptr;
+	cudaGraphExec_t phase_graph_exec[3] = { nullptr, nullptr, nullptr }; // timed mode: local / rhs / solve
 	long iter_graph_launches = 0;
 	cudaEvent_t ev_region[2] = { nullptr, nullptr }; // around the last admmb_step_resident call
 	double last_region_ms = 0.0;
