@@ -45,5 +45,38 @@ def main():
               f"self-sensitivity x_it {res['sens_x_it']:.1e} z_it {res['sens_z_it']:.1e} u_it {res['sens_u_it']:.1e} v {res['sens_v']:.1e}")
 
 
+def shipped():
+    """The reference's four shipped scenes, loaded by the reference's own scene layer (oracle/_ref/scene_export)."""
+    import subprocess
+    import tempfile
+    from scenarios import SHIPPED, SHIPPED_FRAMES, build_shipped, parse_exported_scene
+    exe = os.path.join(ROOT, "oracle", "_ref", "scene_export")
+    if not os.path.exists(exe):
+        print("oracle/_ref/scene_export not built (make -C oracle scene_export): skipping the shipped scenes")
+        return
+    tmp = tempfile.mkdtemp()
+    for name in SHIPPED:
+        txt = os.path.join(tmp, name + ".txt")
+        subprocess.run([exe, name, txt], check=True, stdout=subprocess.DEVNULL)
+        scenes.save_scene(os.path.join(HERE, f"shipped_{name}.scene.npz"), parse_exported_scene(txt, name))
+    for name, sc in build_shipped(HERE).items():
+        ad = RefAdapter(sc["scene"])
+        res = run_scenario(ad, sc, dump=True)
+        ad.close()
+        ad = RefAdapter(sc["scene"])
+        per = run_scenario(ad, sc, dump=True, perturb=1e-15)
+        ad.close()
+        out = dict(x_it=res["x_it"][:1], x=res["x"], v=res["v"][-1:])   # z/u dumps of these scenes are too large to commit
+        for key in ("x_it", "x"):
+            a, g = per[key], res[key]
+            flat = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
+            out["sens_" + key] = np.float64(np.max(np.linalg.norm(flat[0] - flat[1], axis=1) / np.linalg.norm(flat[1], axis=1)))
+        np.savez_compressed(os.path.join(HERE, f"shipped_{name}.ref.npz"), **out)
+        print(f"shipped {name:12s} frames={sc['frames']} nodes={sc['scene']['x'].shape[0]} rows={res['z_it'].shape[2]} "
+              f"self-sensitivity x_it {out['sens_x_it']:.1e} x {out['sens_x']:.1e}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "shipped":
+        main()
+    shipped()

@@ -209,3 +209,157 @@ def build_scenarios():
     a = _anchor_scene()
     S["anchors"] = dict(scene=a, frames=8, events=_anchor_events(a))
     return S
+
+
+# ---- the reference's four shipped scenes (BASELINE.json configs[0..3]) ----------------------------------------
+SHIPPED = ("bunnyexpand", "windyflag", "poordillo", "plinkopony")
+
+
+def parse_exported_scene(path, name):
+    """Text written by oracle/scene_export.cpp (the reference's own scene layer) -> scene dictionary.  Maximal runs
+    of equal forces become batches, in force order."""
+    tok = open(path).read().split()
+    pos = [0]
+
+    def nxt(cast=str):
+        v = tok[pos[0]]
+        pos[0] += 1
+        return cast(v)
+
+    sc = dict(name=name, batches=[], explicit=[])
+    runs = []
+    while pos[0] < len(tok):
+        key = nxt()
+        if key == "settings":
+            sc["dt"], sc["iters"] = nxt(float), nxt(int)
+        elif key == "nodes":
+            n = nxt(int)
+            a = np.array([nxt(float) for _ in range(4 * n)]).reshape(n, 4)
+            sc["x"], sc["m"] = a[:, :3].copy(), a[:, 3].copy()
+        elif key == "x_after":
+            n = nxt(int)
+            sc["x_after_init"] = np.array([nxt(float) for _ in range(3 * n)]).reshape(n, 3)
+        elif key == "forces":
+            nf = nxt(int)
+            for _ in range(nf):
+                t = nxt()
+                if t == "tet":
+                    kind = nxt(int)
+                    idx = [nxt(int) for _ in range(4)]
+                    p0, p1, p2, maxit = nxt(float), nxt(float), nxt(float), nxt(int)
+                    runs.append((("tets", kind, p0, p1, p2, maxit), idx))
+                elif t == "tri":
+                    kind = nxt(int)
+                    idx = [nxt(int) for _ in range(3)]
+                    st, lo, hi, flag = nxt(float), nxt(float), nxt(float), nxt(int)
+                    runs.append((("tris", kind, st, lo, hi, flag), idx))
+                elif t == "bend":
+                    idx = [nxt(int) for _ in range(4)]
+                    runs.append((("bends", nxt(float)), idx))
+                elif t == "spring":
+                    idx = [nxt(int) for _ in range(2)]
+                    runs.append((("springs", nxt(float)), idx))
+                elif t == "sanchor":
+                    i, w = nxt(int), nxt(float)
+                    runs.append((("static_anchors", w), [i]))
+                elif t == "manchor":
+                    i, w = nxt(int), nxt(float)
+                    p = [nxt(float) for _ in range(3)]
+                    runs.append((("moving_anchors", w), [i] + p))
+                elif t == "collision":
+                    w, ns = nxt(float), nxt(int)
+                    kinds, par = [], []
+                    for _ in range(ns):
+                        assert nxt() == "shape"
+                        kinds.append(nxt(int))
+                        par.append([nxt(float) for _ in range(4)])
+                    runs.append((("collision", w), (kinds, par)))
+                else:
+                    raise ValueError(t)
+        elif key == "explicit":
+            ne = nxt(int)
+            for _ in range(ne):
+                t = nxt()
+                d = np.array([nxt(float) for _ in range(3)])
+                if t == "gravity":
+                    sc["explicit"].append(dict(type="gravity", dir=d))
+                else:
+                    nt = nxt(int)
+                    tr = np.array([nxt(int) for _ in range(3 * nt)], dtype=np.int32).reshape(nt, 3)
+                    sc["explicit"].append(dict(type="wind", dir=d, tris=tr))
+        else:
+            raise ValueError(key)
+    # group maximal runs
+    i = 0
+    while i < len(runs):
+        key = runs[i][0]
+        j = i
+        while j < len(runs) and runs[j][0] == key and key[0] != "collision":
+            j += 1
+        j = max(j, i + 1)
+        items = [r[1] for r in runs[i:j]]
+        t = key[0]
+        if t == "tets":
+            sc["batches"].append(dict(type="tets", kind=key[1], idx=np.array(items, dtype=np.int32), p0=key[2], p1=key[3], p2=key[4], maxit=key[5]))
+        elif t == "tris":
+            sc["batches"].append(dict(type="tris", kind=key[1], idx=np.array(items, dtype=np.int32), stiffness=key[2], lmin=key[3], lmax=key[4], flag=key[5]))
+        elif t == "bends":
+            sc["batches"].append(dict(type="bends", idx=np.array(items, dtype=np.int32), stiffness=key[1]))
+        elif t == "springs":
+            sc["batches"].append(dict(type="springs", idx=np.array(items, dtype=np.int32), stiffness=key[1]))
+        elif t == "static_anchors":
+            sc["batches"].append(dict(type="static_anchors", idx=np.array([it[0] for it in items], dtype=np.int32), weight=key[1]))
+        elif t == "moving_anchors":
+            sc["batches"].append(dict(type="moving_anchors", idx=np.array([it[0] for it in items], dtype=np.int32),
+                                      pos=np.array([it[1:] for it in items], dtype=np.float64), weight=key[1]))
+        elif t == "collision":
+            kinds, par = items[0]
+            sc["batches"].append(dict(type="collision", kinds=np.array(kinds, dtype=np.int32), params=np.array(par, dtype=np.float64), weight=key[1]))
+        i = j
+    return sc
+
+
+def _poordillo_events(sc):
+    """Headless stand-in for the GUI interaction of samples/poordillo: the hand sphere's control points are dragged
+    from (.6,.8,.5) towards (2.6,.8,.5) with helper::smooth_move (poordillo.cpp:51-58, AnchorForce.hpp:33-40); at
+    frame 20 the hand is released as the H key does (poordillo.cpp:196-204: active = false, weight = 0,
+    recompute_weights())."""
+    mov = [i for i, b in enumerate(sc["batches"]) if b["type"] == "moving_anchors"]
+    x = sc["x"]
+    hand_c = np.array([.6, .8, .5], dtype=np.float32).astype(np.float64)
+    # the exporter pushed hand anchors first, then foot anchors; they form ONE run (same class), so split by position
+    b = sc["batches"][mov[0]]
+    is_hand = np.linalg.norm(b["pos"] - hand_c, axis=1) < 0.2 + 1e-6
+    start = b["pos"].copy()
+    end = start + np.where(is_hand[:, None], np.array([2.0, 0.0, 0.0]), 0.0)
+    dt = sc["dt"]
+
+    def ev(frame, sim):
+        t = frame * dt
+        if frame < 20:
+            r = min(max(t / 1.2, 0.0), 1.0)
+            sim.set_control_points(mov[0], pos=start + (3.0 * r * r - 2.0 * r * r * r) * (end - start))
+        if frame == 20:
+            act = np.where(is_hand, 0, 1).astype(np.int32)
+            sim.set_control_points(mov[0], active=act)
+            sim.set_anchor_weights(mov[0], np.where(is_hand, 0.0, 1000.0))
+            sim.recompute_weights()
+    return ev
+
+
+SHIPPED_FRAMES = dict(bunnyexpand=12, windyflag=12, poordillo=26, plinkopony=20)
+
+
+def build_shipped(golden_dir):
+    """The four shipped scenes as exported by the reference's scene layer (tests/golden/shipped_*.scene.npz)."""
+    import os
+    S = {}
+    for name in SHIPPED:
+        p = os.path.join(golden_dir, f"shipped_{name}.scene.npz")
+        if not os.path.exists(p):
+            continue
+        sc = scenes.load_scene(p)
+        S[name] = dict(scene=sc, frames=SHIPPED_FRAMES[name])
+        if name == "poordillo":
+            S[name]["events"] = _poordillo_events(sc)
+    return S
