@@ -205,6 +205,10 @@ def build_scenarios():
     area = scenes.cloth_scene(5, 3, springs=False, wind=None, iters=8, name="cloth_area")
     area["batches"][0] = dict(type="tris", kind=TRI_AREA, idx=area["batches"][0]["idx"], stiffness=50.0, lmin=0.9, lmax=1.1, flag=3)
     S["cloth_area"] = dict(scene=area, frames=3)
+    fung = scenes.cloth_scene(5, 3, springs=False, wind=None, iters=8, name="cloth_fung")
+    fung["batches"][0] = dict(type="tris", kind=scenes.TRI_FUNG, idx=fung["batches"][0]["idx"], stiffness=30.0, lmin=0.0, lmax=0.0, flag=0)
+    fung["batches"] = [fung["batches"][0], fung["batches"][2]]   # FungTriangle + static anchors
+    S["cloth_fung"] = dict(scene=fung, frames=3)
     S["collide"] = dict(scene=_collide_scene(), frames=8)
     a = _anchor_scene()
     S["anchors"] = dict(scene=a, frames=8, events=_anchor_events(a))

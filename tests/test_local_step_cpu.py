@@ -62,6 +62,8 @@ class CpuBatch:
             p0, p1, p2, maxit = float(b.get("p0", 0)), float(b.get("p1", 0)), float(b.get("p2", 0)), int(b.get("maxit", 10))
         elif t == 1:
             p0, p1, p2, flag = float(b["stiffness"]), float(b.get("lmin", 0.0)), float(b.get("lmax", 9999999.0)), int(b.get("flag", 1))
+            if self.kind == 2 and self.state is None:
+                self.state = np.ones((self.count, 1))   # FungTriangle: the force's L-BFGS init_hess
         elif t == 2:
             stiff = np.ascontiguousarray(np.broadcast_to(b["stiffness"], (self.count,)), dtype=np.float64)
         elif t == 3:
