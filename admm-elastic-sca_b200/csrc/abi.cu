@@ -53,6 +53,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	drop_iteration_graph(ctx);
 	pcg_destroy(ctx);
 	direct_destroy(ctx);
+	dist_destroy(ctx);
 	for (cudaEvent_t ev : ctx->timing.ev) cudaEventDestroy(ev);
 	for (int k = 0; k < 2; ++k) if (ctx->ev_region[k]) cudaEventDestroy(ctx->ev_region[k]);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -206,10 +207,10 @@ static void to_soa(const std::vector<T> &src, int ncomp, const std::vector<int> 
 }
 
 static int upload_batch_weights(admmb_ctx *ctx, Batch &b) {
-	std::vector<double> w, wdt2(b.count);
+	std::vector<double> w, wdt2(b.nlocal);
 	to_soa(b.w, 1, b.perm, w);
 	const double dt2 = ctx->dt * ctx->dt;
-	for (int p = 0; p < b.count; ++p) wdt2[p] = dt2 * w[p] * w[p];
+	for (int p = 0; p < b.nlocal; ++p) wdt2[p] = dt2 * w[p] * w[p];
 	ADMMB_CUDA(ctx, b.d_w.upload(w, ctx->stream));
 	ADMMB_CUDA(ctx, b.d_wdt2.upload(wdt2, ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -232,15 +233,15 @@ static int upload_batch(admmb_ctx *ctx, Batch &b) {
 		to_soa(b.active, 1, b.perm, act);
 		ADMMB_CUDA(ctx, b.d_active.upload(act, s));
 	}
-	ADMMB_CUDA(ctx, b.d_u.alloc((size_t)b.rows * b.count));
-	ADMMB_CUDA(ctx, b.d_z.alloc((size_t)b.rows * b.count));
+	ADMMB_CUDA(ctx, b.d_u.alloc((size_t)b.rows * b.nlocal));
+	ADMMB_CUDA(ctx, b.d_z.alloc((size_t)b.rows * b.nlocal));
 	ADMMB_CUDA(ctx, b.d_u.zero(s)); // curr_u.setZero()  System.cpp:146
 	ADMMB_CUDA(ctx, b.d_z.zero(s));
 	if (b.nstate) {
 		// HyperElasticTet: last_prox_result = (1,1,1) (TetForce.hpp:127-128), init_hess = 1 (cppoptlib/meta.h:33)
-		std::vector<double> st((size_t)b.nstate * b.count, 1.0);
+		std::vector<double> st((size_t)b.nstate * b.nlocal, 1.0);
 		ADMMB_CUDA(ctx, b.d_state.upload(st, s));
-		ADMMB_CUDA(ctx, b.d_its.alloc(b.count));
+		ADMMB_CUDA(ctx, b.d_its.alloc(b.nlocal));
 		ADMMB_CUDA(ctx, b.d_its.zero(s));
 	}
 	if (b.type == BT_COLLISION) {
@@ -281,13 +282,36 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		for (int i = 0; i < n; ++i) ctx->node_iperm[ctx->node_perm[i]] = i;
 		direct_set_blocks(ctx, blocks); // dissection blocks = supernode partition of the direct solver
 	}
+	// node ownership when the mesh is partitioned over ranks: contiguous chunks of the internal order
+	ctx->chunk = (n + ctx->dist_world - 1) / ctx->dist_world;
+	ctx->own0 = std::min(n, ctx->dist_rank * ctx->chunk);
+	ctx->own1 = std::min(n, ctx->own0 + ctx->chunk);
+	if (ctx->dist_world > 1 && ctx->solver != ADMMB_SOLVER_PCG)
+		ADMMB_FAIL(ctx, ADMMB_E_STATE, "a mesh partitioned over ranks needs ADMMB_SOLVER_PCG (sparse triangular solves do not shard: replicas only)");
 	long row = 0, slot = 0;
 	for (Batch &b : ctx->batches) {
 		if (b.type == BT_COLLISION) { b.perm = ctx->node_perm; }
-		else morton_order_elements(ctx, b);
+		else {
+			morton_order_elements(ctx, b);
+			if (ctx->dist_world > 1) {
+				// keep the forces that touch an owned node: their contributions complete the owned rows of the right-hand
+				// side without any exchange (boundary forces are evaluated on both sides, deterministically)
+				std::vector<int> keep;
+				for (int e : b.perm) {
+					bool mine = false;
+					for (int c = 0; c < b.nv && !mine; ++c) {
+						const int v = ctx->node_iperm[b.idx[(size_t)e * b.nv + c]];
+						mine = (v >= ctx->own0 && v < ctx->own1);
+					}
+					if (mine) keep.push_back(e);
+				}
+				b.perm.swap(keep);
+			}
+		}
+		b.nlocal = (int)b.perm.size();
 		b.row_base = row; b.slot_base = slot;
 		row += (long)b.rows * b.count;
-		slot += (long)b.nv * b.count;
+		slot += (long)b.nv * b.nlocal;
 		int rc = upload_batch(ctx, b);
 		if (rc) return rc;
 	}
@@ -299,12 +323,12 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 	{
 		std::vector<int> vptr(n + 1, 0), vslots((size_t)slot);
 		for (const Batch &b : ctx->batches)
-			for (int p = 0; p < b.count; ++p)
+			for (int p = 0; p < b.nlocal; ++p)
 				for (int c = 0; c < b.nv; ++c) vptr[ctx->node_iperm[b.idx[(size_t)b.perm[p] * b.nv + c]] + 1]++;
 		for (int i = 0; i < n; ++i) vptr[i + 1] += vptr[i];
 		std::vector<int> fill(vptr.begin(), vptr.end() - 1);
 		for (const Batch &b : ctx->batches)
-			for (int p = 0; p < b.count; ++p)
+			for (int p = 0; p < b.nlocal; ++p)
 				for (int c = 0; c < b.nv; ++c) {
 					const int v = ctx->node_iperm[b.idx[(size_t)b.perm[p] * b.nv + c]];
 					vslots[fill[v]++] = (int)(b.slot_base + (long)p * b.nv + c);
@@ -316,7 +340,8 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 	}
 	// node vectors
 	{
-		std::vector<double> xi(3 * (size_t)n), mi(n);
+		const size_t npad = (size_t)ctx->chunk * ctx->dist_world; // >= n; padding keeps the all-gather chunks equal
+		std::vector<double> xi(3 * npad, 0.0), mi(n);
 		for (int i = 0; i < n; ++i) {
 			const int u = ctx->node_perm[i];
 			for (int j = 0; j < 3; ++j) xi[3 * (size_t)i + j] = ctx->h_x0[3 * (size_t)u + j];
@@ -325,12 +350,12 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		ADMMB_CUDA(ctx, ctx->d_x.upload(xi, s));
 		ADMMB_CUDA(ctx, ctx->d_m.upload(mi, s));
 		ADMMB_CUDA(ctx, ctx->d_node_perm.upload(ctx->node_perm, s));
-		ADMMB_CUDA(ctx, ctx->d_v.alloc(3 * (size_t)n));
+		ADMMB_CUDA(ctx, ctx->d_v.alloc(3 * npad));
 		ADMMB_CUDA(ctx, ctx->d_v.zero(s)); // m_v.setZero()  System.cpp:113
-		ADMMB_CUDA(ctx, ctx->d_xbar.alloc(3 * (size_t)n));
-		ADMMB_CUDA(ctx, ctx->d_Mxbar.alloc(3 * (size_t)n));
+		ADMMB_CUDA(ctx, ctx->d_xbar.alloc(3 * npad));
+		ADMMB_CUDA(ctx, ctx->d_Mxbar.alloc(3 * npad));
 		ADMMB_CUDA(ctx, ctx->d_currx.upload(xi, s));
-		ADMMB_CUDA(ctx, ctx->d_b.alloc(3 * (size_t)n));
+		ADMMB_CUDA(ctx, ctx->d_b.alloc(3 * npad));
 		ADMMB_CUDA(ctx, ctx->d_io.alloc(6 * (size_t)n));
 		ADMMB_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, 6 * (size_t)n * sizeof(double)));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -620,11 +645,11 @@ static int check_batch(admmb_ctx *ctx, int batch) {
 }
 
 static int sync_anchor_targets_from_device(admmb_ctx *ctx, Batch &b) {
-	std::vector<double> soa((size_t)3 * b.count);
+	std::vector<double> soa((size_t)3 * b.nlocal);
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(soa.data(), b.d_aux.p, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	for (int k = 0; k < 3; ++k)
-		for (int p = 0; p < b.count; ++p) b.aux[(size_t)b.perm[p] * 3 + k] = soa[(size_t)k * b.count + p];
+		for (int p = 0; p < b.nlocal; ++p) b.aux[(size_t)b.perm[p] * 3 + k] = soa[(size_t)k * b.nlocal + p];
 	return ADMMB_OK;
 }
 
@@ -711,18 +736,18 @@ extern "C" long admmb_state_size(admmb_ctx *ctx, int which) {
 }
 
 static int soa_download(admmb_ctx *ctx, const Batch &b, const double *d, int ncomp, double *out_aos) {
-	std::vector<double> soa((size_t)ncomp * b.count);
+	std::vector<double> soa((size_t)ncomp * b.nlocal);
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(soa.data(), d, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	for (int k = 0; k < ncomp; ++k)
-		for (int p = 0; p < b.count; ++p) out_aos[(size_t)b.perm[p] * ncomp + k] = soa[(size_t)k * b.count + p];
+		for (int p = 0; p < b.nlocal; ++p) out_aos[(size_t)b.perm[p] * ncomp + k] = soa[(size_t)k * b.nlocal + p];
 	return ADMMB_OK;
 }
 
 static int soa_upload(admmb_ctx *ctx, const Batch &b, double *d, int ncomp, const double *in_aos) {
-	std::vector<double> soa((size_t)ncomp * b.count);
+	std::vector<double> soa((size_t)ncomp * b.nlocal);
 	for (int k = 0; k < ncomp; ++k)
-		for (int p = 0; p < b.count; ++p) soa[(size_t)k * b.count + p] = in_aos[(size_t)b.perm[p] * ncomp + k];
+		for (int p = 0; p < b.nlocal; ++p) soa[(size_t)k * b.nlocal + p] = in_aos[(size_t)b.perm[p] * ncomp + k];
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(d, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ADMMB_OK;
@@ -760,10 +785,10 @@ extern "C" int admmb_get_state(admmb_ctx *ctx, int which, double *out) {
 		long o = 0;
 		for (const Batch &b : ctx->batches) {
 			if (!is_hyper(b) || b.count == 0) continue;
-			std::vector<int> its(b.count);
+			std::vector<int> its(b.nlocal);
 			ADMMB_CUDA(ctx, cudaMemcpyAsync(its.data(), b.d_its.p, its.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 			ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			for (int p = 0; p < b.count; ++p) out[o + b.perm[p]] = (double)its[p];
+			for (int p = 0; p < b.nlocal; ++p) out[o + b.perm[p]] = (double)its[p];
 			o += b.count;
 		}
 		return ADMMB_OK;

@@ -49,6 +49,7 @@ struct DevBuf {
 struct Batch {
 	int type = 0, kind = 0;
 	int count = 0;  // number of forces
+	int nlocal = 0; // forces resident on this device (= count unless the mesh is partitioned over ranks); = perm.size()
 	int nv = 0;     // nodes per force
 	int rows = 0;   // live rows of D per force
 	int nsel = 0;   // selector coefficients per force stored in S (tets 12, tris 6, others 0)
@@ -81,7 +82,7 @@ struct Batch {
 	DevBuf<double> d_shape_params;
 };
 
-struct DirectSolver; // direct_solve.h
+struct DirectSolver; // direct_solve.cu
 struct PcgSolver;    // kernels_global.cu
 
 struct Timing {
@@ -138,6 +139,11 @@ struct admmb_ctx {
 	long cg_iters_total = 0;
 	double factor_seconds = 0.0;
 	admmb::Timing timing;
+
+	// single mesh partitioned over ranks (PCG only): replicated setup, owned node range [own0, own1) of the internal order
+	int dist_rank = 0, dist_world = 1;
+	int own0 = 0, own1 = 0, chunk = 0;  // chunk = ceil(n / world); node vectors are allocated world * chunk long
+	void *nccl_comm = nullptr;
 	bool use_graph = true;
 	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)
 	cudaGraphExec_t iter_graph_exec = nullptr;
@@ -183,6 +189,10 @@ int launch_permute_out(admmb_ctx *ctx, const double *d_src_internal, double *d_d
 int pcg_setup(admmb_ctx *ctx);
 int pcg_solve(admmb_ctx *ctx);
 void pcg_destroy(admmb_ctx *ctx);
+// dist.cu
+int dist_allgather_nodes(admmb_ctx *ctx, double *vec);            // in place: every rank contributes its owned rows
+int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count);
+void dist_destroy(admmb_ctx *ctx);
 // direct_solve.cu
 void direct_set_blocks(admmb_ctx *ctx, const std::vector<int> &block_end);
 void direct_fill_info(const admmb_ctx *ctx, admmb_info *out);

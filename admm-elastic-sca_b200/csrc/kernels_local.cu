@@ -64,17 +64,17 @@ __global__ void __launch_bounds__(LOCAL_THREADS) k_local_collision(const LocalAr
 
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 	(void)dt2;
-	if (b.count == 0) return ADMMB_OK;
+	if (b.nlocal == 0) return ADMMB_OK;
 	LocalArgs a;
 	memset(&a, 0, sizeof(a));
-	a.count = b.count;
+	a.count = b.nlocal;
 	a.idx = b.d_idx.p; a.S = b.d_S.p; a.w = b.d_w.p; a.wdt2 = b.d_wdt2.p; a.kk = b.d_kk.p; a.aux = b.d_aux.p;
 	a.u = b.d_u.p; a.z = b.d_z.p; a.state = b.d_state.p; a.its = b.d_its.p; a.active = b.d_active.p;
 	a.x = d_x;
 	a.P = ctx->d_P.p + 3 * (size_t)b.slot_base;
 	a.p0 = b.p0; a.p1 = b.p1; a.p2 = b.p2; a.max_iterations = b.max_iterations; a.flag = b.flag;
 	a.shape_kind = b.d_shape_kind.p; a.shape_params = b.d_shape_params.p; a.nshapes = (int)b.shape_kind.size();
-	const int grid = (b.count + LOCAL_THREADS - 1) / LOCAL_THREADS;
+	const int grid = (b.nlocal + LOCAL_THREADS - 1) / LOCAL_THREADS;
 	cudaStream_t s = ctx->stream;
 	switch (b.type) {
 	case BT_TETS:
@@ -82,13 +82,13 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 		case ADMMB_TET_LINEAR_STRAIN: k_local_tets<ADMMB_TET_LINEAR_STRAIN, 1><<<grid, LOCAL_THREADS, 0, s>>>(a); break;
 		case ADMMB_TET_VOLUME: k_local_tets<ADMMB_TET_VOLUME, 1><<<grid, LOCAL_THREADS, 0, s>>>(a); break;
 		case ADMMB_TET_NEOHOOKEAN: {
-			const int g = (b.count + HYPER_THREADS - 1) / HYPER_THREADS;
+			const int g = (b.nlocal + HYPER_THREADS - 1) / HYPER_THREADS;
 			if (b.max_iterations <= 5) k_local_tets_hyper<NHModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
 			else k_local_tets_hyper<NHModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
 			break;
 		}
 		case ADMMB_TET_STVK: {
-			const int g = (b.count + HYPER_THREADS - 1) / HYPER_THREADS;
+			const int g = (b.nlocal + HYPER_THREADS - 1) / HYPER_THREADS;
 			if (b.max_iterations <= 5) k_local_tets_hyper<StVKModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
 			else k_local_tets_hyper<StVKModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
 			break;
