@@ -1,0 +1,71 @@
+// dist.cu -- single mesh partitioned over several GPUs (one process per GPU), SURVEY.md 8(e) rows 2 and 3.
+//
+// Setup is replicated: every rank is given the whole scene, computes the same nested-dissection order, and OWNS the
+// contiguous chunk [own0, own1) of it.  Per ADMM iteration a rank
+//   * runs the local step for the forces that touch an owned node (boundary forces are evaluated on both sides,
+//     bit-identically, so the owned rows of the right-hand side are complete without any exchange),
+//   * runs Jacobi-PCG on its rows of A_n; the only data-path collectives are an all-gather of the search direction p
+//     before each SpMV (each rank contributes its owned rows; over NVSwitch this is the halo exchange in its simplest
+//     form -- 3 n doubles in total, 4.2 MB at 1 M tets) and all-reduces of 3 / 6 doubles for the dot products,
+//   * all-gathers the solution so that every rank holds curr_x for the next local step.
+// x and v stay replicated (frame begin / end are evaluated redundantly), so the C ABI is unchanged: every rank makes
+// the same calls with the same data.  The direct solver does not shard (sparse triangular solves are a dependency
+// chain): admmb_finalize rejects it for world > 1 -- replicas only.
+#include <nccl.h>
+
+#include "common.h"
+
+using namespace admmb;
+
+#define ADMMB_NCCL(ctx, call)                                                                                        \
+	do {                                                                                                             \
+		ncclResult_t _r = (call);                                                                                    \
+		if (_r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+	} while (0)
+
+extern "C" int admmb_dist_unique_id(char *out128) {
+	if (!out128) return ADMMB_E_ARG;
+	ncclUniqueId id;
+	if (ncclGetUniqueId(&id) != ncclSuccess) return ADMMB_E_CUDA;
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+	memcpy(out128, &id, sizeof(id));
+	return ADMMB_OK;
+}
+
+extern "C" int admmb_dist_init(admmb_ctx *ctx, int rank, int world, const char *id128) {
+	if (!ctx) return ADMMB_E_ARG;
+	cudaSetDevice(ctx->device);
+	if (ctx->finalized) ADMMB_FAIL(ctx, ADMMB_E_STATE, "admmb_dist_init must precede admmb_finalize");
+	if (world < 1 || rank < 0 || rank >= world || !id128) ADMMB_FAIL(ctx, ADMMB_E_ARG, "bad rank / world / id");
+	ctx->dist_rank = rank;
+	ctx->dist_world = world;
+	if (world == 1) return ADMMB_OK;
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	ncclComm_t comm;
+	ADMMB_NCCL(ctx, ncclCommInitRank(&comm, world, id, rank));
+	ctx->nccl_comm = (void *)comm;
+	return ADMMB_OK;
+}
+
+namespace admmb {
+
+int dist_allgather_nodes(admmb_ctx *ctx, double *vec) {
+	if (ctx->dist_world == 1) return ADMMB_OK;
+	const size_t cnt = 3 * (size_t)ctx->chunk;
+	ADMMB_NCCL(ctx, ncclAllGather(vec + cnt * ctx->dist_rank, vec, cnt, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return ADMMB_OK;
+}
+
+int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count) {
+	if (ctx->dist_world == 1) return ADMMB_OK;
+	ADMMB_NCCL(ctx, ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return ADMMB_OK;
+}
+
+void dist_destroy(admmb_ctx *ctx) {
+	if (ctx->nccl_comm) ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
+	ctx->nccl_comm = nullptr;
+}
+
+} // namespace admmb

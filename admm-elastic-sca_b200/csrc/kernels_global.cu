@@ -122,13 +122,18 @@ struct PcgSolver {
 	DevBuf<int> ptr, idx;
 	DevBuf<double> val, dinv;
 	DevBuf<double> r, p, Ap;
-	DevBuf<double> scal; // [0..5] pAp[2][3], [6..11] rz[2][3], [12..17] rr[2][3], [18..20] bb[3]
+	DevBuf<double> scal; // [0..5] pAp[2][3]; parity q: rz[3] at 6+6q, rr[3] at 9+6q (adjacent: one all-reduce); [18..20] bb[3]; [21] best rr
 	DevBuf<int> flag;    // [0] done, [1] iterations used, [2] iterations without progress
 	int *h_flag = nullptr;
 	int grid = 0;
 };
 
 #define PCG_THREADS 256
+#define S_PAP(q) (3 * (q))
+#define S_RZ(q) (6 + 6 * (q))
+#define S_RR(q) (9 + 6 * (q))
+#define S_BB 18
+#define S_BEST 21
 
 __device__ __forceinline__ void block_reduce3_atomic(double a0, double a1, double a2, double *dst) {
 	__shared__ double sh[3][PCG_THREADS / 32];
@@ -155,19 +160,20 @@ __device__ __forceinline__ void block_reduce3_atomic(double a0, double a1, doubl
 }
 
 // r = b - A x; p = Dinv r; rz[0] = r.p; rr[0] = r.r; bb = b.b
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int n, const int *__restrict__ ptr, const int *__restrict__ idx,
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const int *__restrict__ ptr, const int *__restrict__ idx,
                                                           const double *__restrict__ val, const double *__restrict__ dinv,
                                                           const double *__restrict__ b, const double *__restrict__ x,
                                                           double *__restrict__ r, double *__restrict__ p, double *scal) {
+	// rows [r0, n) of this rank; ptr / dinv are indexed by the local row (i - r0), everything else by the global node
 	double rz[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 }, bb[3] = { 0, 0, 0 };
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
-		for (int q = ptr[i]; q < ptr[i + 1]; ++q) {
+		for (int q = ptr[i - r0]; q < ptr[i - r0 + 1]; ++q) {
 			const double av = val[q];
 			const double *xc = x + 3 * (size_t)idx[q];
 			a[0] += av * xc[0]; a[1] += av * xc[1]; a[2] += av * xc[2];
 		}
-		const double di = dinv[i];
+		const double di = dinv[i - r0];
 		for (int j = 0; j < 3; ++j) {
 			const double bj = b[3 * (size_t)i + j];
 			const double rj = bj - a[j];
@@ -177,54 +183,54 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int n, const int *__re
 			rz[j] += rj * zj; rr[j] += rj * rj; bb[j] += bj * bj;
 		}
 	}
-	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + 6);
-	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + 12);
-	block_reduce3_atomic(bb[0], bb[1], bb[2], scal + 18);
+	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + S_RZ(0));
+	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_RR(0));
+	block_reduce3_atomic(bb[0], bb[1], bb[2], scal + S_BB);
 }
 
 __global__ void k_pcg_check0(double *scal, int *flag, double tol2) {
 	// converged before the first iteration?
 	bool done = true;
-	for (int j = 0; j < 3; ++j) done = done && (scal[12 + j] <= tol2 * scal[18 + j]);
+	for (int j = 0; j < 3; ++j) done = done && (scal[S_RR(0) + j] <= tol2 * scal[S_BB + j]);
 	flag[0] = done ? 1 : 0;
 	flag[1] = 0;
 	flag[2] = 0;
 }
 
 // Ap = A p; pAp[k&1] += p.Ap; zero the accumulators the rest of this iteration adds into
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int n, int k, const int *__restrict__ ptr, const int *__restrict__ idx,
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int k, const int *__restrict__ ptr, const int *__restrict__ idx,
                                                           const double *__restrict__ val, const double *__restrict__ p,
                                                           double *__restrict__ Ap, double *scal, const int *flag) {
 	if (flag[0]) return;
 	const int cur = k & 1, nxt = cur ^ 1;
 	double s[3] = { 0, 0, 0 };
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
-		for (int q = ptr[i]; q < ptr[i + 1]; ++q) {
+		for (int q = ptr[i - r0]; q < ptr[i - r0 + 1]; ++q) {
 			const double av = val[q];
 			const double *pc = p + 3 * (size_t)idx[q];
 			a[0] += av * pc[0]; a[1] += av * pc[1]; a[2] += av * pc[2];
 		}
 		for (int j = 0; j < 3; ++j) { Ap[3 * (size_t)i + j] = a[j]; s[j] += a[j] * p[3 * (size_t)i + j]; }
 	}
-	if (blockIdx.x == 0 && threadIdx.x < 3) { scal[6 + 3 * nxt + threadIdx.x] = 0.0; scal[12 + 3 * nxt + threadIdx.x] = 0.0; }
-	block_reduce3_atomic(s[0], s[1], s[2], scal + 3 * cur);
+	if (blockIdx.x == 0 && threadIdx.x < 3) { scal[S_RZ(nxt) + threadIdx.x] = 0.0; scal[S_RR(nxt) + threadIdx.x] = 0.0; }
+	block_reduce3_atomic(s[0], s[1], s[2], scal + S_PAP(cur));
 }
 
 // alpha = rz/pAp; x += alpha p; r -= alpha Ap; rz[nxt] += r.Dinv r; rr[nxt] += r.r
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int n, int k, const double *__restrict__ dinv, const double *__restrict__ p,
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int k, const double *__restrict__ dinv, const double *__restrict__ p,
                                                             const double *__restrict__ Ap, double *__restrict__ x,
                                                             double *__restrict__ r, double *scal, const int *flag) {
 	if (flag[0]) return;
 	const int cur = k & 1, nxt = cur ^ 1;
 	double alpha[3];
 	for (int j = 0; j < 3; ++j) {
-		const double pAp = scal[3 * cur + j];
-		alpha[j] = (pAp > 0.0) ? scal[6 + 3 * cur + j] / pAp : 0.0;
+		const double pAp = scal[S_PAP(cur) + j];
+		alpha[j] = (pAp > 0.0) ? scal[S_RZ(cur) + j] / pAp : 0.0;
 	}
 	double rz[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 };
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-		const double di = dinv[i];
+	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const double di = dinv[i - r0];
 		for (int j = 0; j < 3; ++j) {
 			const size_t t = 3 * (size_t)i + j;
 			x[t] += alpha[j] * p[t];
@@ -233,25 +239,25 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int n, int k, const 
 			rz[j] += rj * (di * rj); rr[j] += rj * rj;
 		}
 	}
-	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + 6 + 3 * nxt);
-	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + 12 + 3 * nxt);
+	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + S_RZ(nxt));
+	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_RR(nxt));
 }
 
 // beta = rz_new/rz_old; p = Dinv r + beta p; convergence test; zero pAp for the next iteration
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int n, int k, const double *__restrict__ dinv, const double *__restrict__ r,
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int r0, int n, int k, const double *__restrict__ dinv, const double *__restrict__ r,
                                                                double *__restrict__ p, double *scal, int *flag, double tol2) {
 	if (flag[0]) return;
 	const int cur = k & 1, nxt = cur ^ 1;
 	double beta[3];
 	bool done = true;
 	for (int j = 0; j < 3; ++j) {
-		const double o = scal[6 + 3 * cur + j];
-		beta[j] = (o > 0.0) ? scal[6 + 3 * nxt + j] / o : 0.0;
-		done = done && (scal[12 + 3 * nxt + j] <= tol2 * scal[18 + j]);
+		const double o = scal[S_RZ(cur) + j];
+		beta[j] = (o > 0.0) ? scal[S_RZ(nxt) + j] / o : 0.0;
+		done = done && (scal[S_RR(nxt) + j] <= tol2 * scal[S_BB + j]);
 	}
 	if (!done) {
-		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-			const double di = dinv[i];
+		for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+			const double di = dinv[i - r0];
 			for (int j = 0; j < 3; ++j) {
 				const size_t t = 3 * (size_t)i + j;
 				p[t] = di * r[t] + beta[j] * p[t];
@@ -261,11 +267,11 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int n, int k, con
 	// All blocks have read scal[*cur*] above only through registers; the writes below touch slots that no
 	// block of THIS kernel reads (pAp[nxt]) or that are only read by later kernels (flag).
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		scal[3 * nxt + 0] = 0.0; scal[3 * nxt + 1] = 0.0; scal[3 * nxt + 2] = 0.0;
+		scal[S_PAP(nxt) + 0] = 0.0; scal[S_PAP(nxt) + 1] = 0.0; scal[S_PAP(nxt) + 2] = 0.0;
 		flag[1] = k + 1;
 		// stagnation guard: once the residual sits at rounding level CG must not be iterated further
-		const double rr = scal[12 + 3 * nxt] + scal[12 + 3 * nxt + 1] + scal[12 + 3 * nxt + 2];
-		if (k == 0 || rr < 0.99 * scal[21]) { scal[21] = rr; flag[2] = 0; }
+		const double rr = scal[S_RR(nxt)] + scal[S_RR(nxt) + 1] + scal[S_RR(nxt) + 2];
+		if (k == 0 || rr < 0.99 * scal[S_BEST]) { scal[S_BEST] = rr; flag[2] = 0; }
 		else if (++flag[2] >= 25 || !(rr == rr)) flag[0] = 1;
 	}
 	if (done && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) flag[0] = 1;
@@ -274,48 +280,66 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int n, int k, con
 int pcg_setup(admmb_ctx *ctx) {
 	if (!ctx->pcg) ctx->pcg = new PcgSolver();
 	PcgSolver &S = *ctx->pcg;
-	const int n = ctx->n;
-	std::vector<double> dinv(n, 1.0);
-	for (int i = 0; i < n; ++i)
-		for (int q = ctx->A_ptr[i]; q < ctx->A_ptr[i + 1]; ++q)
+	const int n = ctx->n, r0 = ctx->own0, r1 = ctx->own1;
+	// this rank's rows of A_n (all rows when the mesh is not partitioned); column indices stay global
+	std::vector<int> ptr(1, 0), idx;
+	std::vector<double> val, dinv(std::max(r1 - r0, 1), 1.0);
+	for (int i = r0; i < r1; ++i) {
+		for (int q = ctx->A_ptr[i]; q < ctx->A_ptr[i + 1]; ++q) {
+			idx.push_back(ctx->A_idx[q]);
+			val.push_back(ctx->A_val[q]);
 			if (ctx->A_idx[q] == i) {
 				if (!(ctx->A_val[q] > 0.0)) ADMMB_FAIL(ctx, ADMMB_E_NUMERIC, "system matrix has a non-positive diagonal at node %d (zero mass?)", ctx->node_perm[i]);
-				dinv[i] = 1.0 / ctx->A_val[q];
+				dinv[i - r0] = 1.0 / ctx->A_val[q];
 			}
-	ADMMB_CUDA(ctx, S.ptr.upload(ctx->A_ptr, ctx->stream));
-	ADMMB_CUDA(ctx, S.idx.upload(ctx->A_idx, ctx->stream));
-	ADMMB_CUDA(ctx, S.val.upload(ctx->A_val, ctx->stream));
+		}
+		ptr.push_back((int)idx.size());
+	}
+	if (idx.empty()) { idx.push_back(0); val.push_back(0.0); }
+	const size_t npad = 3 * (size_t)ctx->chunk * ctx->dist_world;
+	ADMMB_CUDA(ctx, S.ptr.upload(ptr, ctx->stream));
+	ADMMB_CUDA(ctx, S.idx.upload(idx, ctx->stream));
+	ADMMB_CUDA(ctx, S.val.upload(val, ctx->stream));
 	ADMMB_CUDA(ctx, S.dinv.upload(dinv, ctx->stream));
-	ADMMB_CUDA(ctx, S.r.alloc(3 * (size_t)n));
-	ADMMB_CUDA(ctx, S.p.alloc(3 * (size_t)n));
-	ADMMB_CUDA(ctx, S.Ap.alloc(3 * (size_t)n));
+	ADMMB_CUDA(ctx, S.r.alloc(npad));
+	ADMMB_CUDA(ctx, S.p.alloc(npad));
+	ADMMB_CUDA(ctx, S.Ap.alloc(npad));
+	ADMMB_CUDA(ctx, S.p.zero(ctx->stream));
 	ADMMB_CUDA(ctx, S.scal.alloc(24));
 	ADMMB_CUDA(ctx, S.flag.alloc(4));
 	if (!S.h_flag) ADMMB_CUDA(ctx, cudaMallocHost((void **)&S.h_flag, 2 * sizeof(int)));
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	const int want = (n + PCG_THREADS - 1) / PCG_THREADS;
+	const int want = (r1 - r0 + PCG_THREADS - 1) / PCG_THREADS;
 	S.grid = want < sms * 4 ? (want > 0 ? want : 1) : sms * 4;
+	(void)n;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ADMMB_OK;
 }
 
 int pcg_solve(admmb_ctx *ctx) {
 	PcgSolver &S = *ctx->pcg;
-	const int n = ctx->n;
+	const int r0 = ctx->own0, r1 = ctx->own1;
 	cudaStream_t s = ctx->stream;
 	const double tol2 = ctx->cg_tol * ctx->cg_tol;
+	int rc;
 	ADMMB_CUDA(ctx, S.scal.zero(s));
-	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(n, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.p.p, S.scal.p);
+	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.p.p, S.scal.p);
+	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_RZ(0), 15))) return rc; // rz[0], rr[0], (rz[1], rr[1] still zero), bb
+	if ((rc = dist_allgather_nodes(ctx, S.p.p))) return rc;
 	k_pcg_check0<<<1, 1, 0, s>>>(S.scal.p, S.flag.p, tol2);
 	ctx->launches += 2;
 	const int chunk = 32;
 	int k = 0;
 	while (k < ctx->cg_max_iters) {
 		for (int c = 0; c < chunk && k < ctx->cg_max_iters; ++c, ++k) {
-			k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(n, k, S.ptr.p, S.idx.p, S.val.p, S.p.p, S.Ap.p, S.scal.p, S.flag.p);
-			k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(n, k, S.dinv.p, S.p.p, S.Ap.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p);
-			k_pcg_direction<<<S.grid, PCG_THREADS, 0, s>>>(n, k, S.dinv.p, S.r.p, S.p.p, S.scal.p, S.flag.p, tol2);
+			const int cur = k & 1, nxt = cur ^ 1;
+			k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.ptr.p, S.idx.p, S.val.p, S.p.p, S.Ap.p, S.scal.p, S.flag.p);
+			if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_PAP(cur), 3))) return rc;
+			k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.dinv.p, S.p.p, S.Ap.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p);
+			if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_RZ(nxt), 6))) return rc;
+			k_pcg_direction<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.dinv.p, S.r.p, S.p.p, S.scal.p, S.flag.p, tol2);
+			if ((rc = dist_allgather_nodes(ctx, S.p.p))) return rc;
 			ctx->launches += 3;
 		}
 		ADMMB_CUDA(ctx, cudaMemcpyAsync(S.h_flag, S.flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -323,6 +347,8 @@ int pcg_solve(admmb_ctx *ctx) {
 		if (S.h_flag[0]) break;
 	}
 	ctx->cg_iters_total += S.h_flag[1];
+	// every rank needs the whole iterate for the next local step
+	if ((rc = dist_allgather_nodes(ctx, ctx->d_currx.p))) return rc;
 	ADMMB_CUDA(ctx, cudaGetLastError());
 	return ADMMB_OK;
 }

@@ -26,7 +26,7 @@ EXPORTS = [
     "admmb_step_dump", "admmb_debug_local_step", "admmb_debug_global_step", "admmb_step_resident", "admmb_upload_xv", "admmb_download_xv", "admmb_update_anchor_targets",
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
-    "admmb_timing_read", "admmb_last_region_ms",
+    "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
 ]
 
 
@@ -84,6 +84,8 @@ def lib():
     L.admmb_timing_enable.argtypes = [vp, C.c_int]
     L.admmb_timing_read.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
     L.admmb_last_region_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.admmb_dist_unique_id.argtypes = [C.c_char_p]
+    L.admmb_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     _lib = L
     return L
 
@@ -107,7 +109,8 @@ class System:
     recompute_weights().  Built from a scene dictionary (scenes.py).
     """
 
-    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None):
+    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None):
+        """dist = (rank, world, id128 bytes) partitions the mesh over `world` processes (PCG only)."""
         L = lib()
         self.L = L
         h = C.c_void_p()
@@ -168,6 +171,8 @@ class System:
         else:
             self.host_explicit = list(ex)
         self._ck(L.admmb_set_solver(h, int(solver), float(cg_tol), int(cg_max_iters)))
+        if dist is not None:
+            self._ck(L.admmb_dist_init(h, int(dist[0]), int(dist[1]), dist[2]))
         self._ck(L.admmb_finalize(h, self.dt))
 
     def _ck(self, rc):
@@ -297,6 +302,15 @@ class System:
         it = C.c_long(0)
         self._ck(self.L.admmb_timing_read(self.h, ms, C.byref(it), 1 if reset else 0))
         return dict(local_ms=ms[0], rhs_ms=ms[1], solve_ms=ms[2], step_ms=ms[3], iters=it.value)
+
+
+def dist_unique_id():
+    """ncclUniqueId (128 bytes) to be created on rank 0 and handed to every rank's System(dist=...)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().admmb_dist_unique_id(buf)
+    if rc != 0:
+        raise AdmmError(f"admmb_dist_unique_id failed ({rc})")
+    return buf.raw
 
 
 def wind_project(x, v, tris, direction, dt):

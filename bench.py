@@ -35,7 +35,7 @@ UNIT = "ADMM iterations/s"
 ADMM_ITERS = 10
 FULL_TETS = 998250  # N = 55
 EXEC_FP64_FLOPS_PER_TET_ITER = 8990      # profiles/r1b_local.txt (steady state): (1018.7 + 1216.2 + 2 x 1309.3) flops/clk x 1.85 Mclk / 998250 tets
-SOLVE_DRAM_BYTES_NCU = 1.710e9           # profiles/r1a_solve.txt: dram bytes read+written by the 28 launches of one solve
+SOLVE_DRAM_BYTES_NCU = 1.685e9           # profiles/r1c_solve.txt: dram bytes read+written by the 28 launches of one solve
 
 
 def peaks():
@@ -257,7 +257,7 @@ def main():
                 "frac": solve_gbs / hbm_peak, "traffic": SOLVE_DRAM_BYTES_NCU, "peak_source": peak_src,
                 "share_of_step": solve_ms / (local_ms + rhs_ms + solve_ms),
                 "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; "
-                        f"{info0['n_levels']} levels; traffic = dram bytes of the 28 launches summed, ncu profiles/r1a_solve.txt"}
+                        f"{info0['n_levels']} levels; traffic = dram bytes of the 28 launches summed, ncu profiles/r1c_solve.txt"}
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
         fp64_peak = 148 * 64 * 2 * sm_clock / 1e12   # 64 DFMA lanes per SM per clock (ncu: sm__sass_thread_inst_executed_op_dfma peak)
         local_tflops = EXEC_FP64_FLOPS_PER_TET_ITER * ntets / (local_ms * 1e-3) / 1e12 if local_ms > 0 else 0.0

@@ -92,6 +92,14 @@ int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3);
 /* Solver choice and tolerances; call before admmb_finalize.  tol and max_cg_iters apply to PCG only. */
 int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters);
 
+/* One mesh partitioned over several GPUs, one process per GPU (PCG solver only; the direct solve does not shard --
+ * replicas only).  Rank 0 creates an id with admmb_dist_unique_id (an ncclUniqueId, 128 bytes) and distributes it out
+ * of band; every rank then calls admmb_dist_init before admmb_finalize and afterwards makes the SAME calls with the
+ * SAME data as in the single-GPU case: setup, x and v are replicated, the local step and the rows of the solve are
+ * partitioned, NCCL carries the all-gather of the CG search direction / solution and the dot-product all-reduces. */
+int admmb_dist_unique_id(char *out128);
+int admmb_dist_init(admmb_ctx *ctx, int rank, int world, const char *id128);
+
 /* Replaces System::initialize() (System.cpp:98-156): computes rest shapes / weights from the node positions
  * given to admmb_set_nodes, builds A = M + dt^2 D^T W^2 D in its scalar n x n form, orders and factors it
  * (direct) or builds the preconditioner (PCG), uploads everything and zeroes u and v. */
