@@ -11,22 +11,56 @@
 // x and v stay replicated (frame begin / end are evaluated redundantly), so the C ABI is unchanged: every rank makes
 // the same calls with the same data.  The direct solver does not shard (sparse triangular solves are a dependency
 // chain): admmb_finalize rejects it for world > 1 -- replicas only.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include "common.h"
 
 using namespace admmb;
 
+// NCCL is resolved at run time (dlopen) instead of being a link-time dependency of libadmm_b200.so: a process that
+// also imports PyTorch must end up with ONE libnccl.so.2, and PyTorch's bundled build is newer than the system one
+// (loading the system library first breaks `import torch`).  dlopen by soname returns whichever copy the process
+// already holds, or the system library otherwise.  Single-GPU use never touches NCCL.
+namespace {
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+} g_nccl;
+
+bool nccl_load() {
+	if (g_nccl.ok) return true;
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return false;
+	g_nccl.handle = h;
+	g_nccl.GetUniqueId = (ncclResult_t(*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+	g_nccl.CommInitRank = (ncclResult_t(*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+	g_nccl.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+	g_nccl.AllGather = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+	g_nccl.AllReduce = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+	g_nccl.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString;
+	return g_nccl.ok;
+}
+} // namespace
+
 #define ADMMB_NCCL(ctx, call)                                                                                        \
 	do {                                                                                                             \
 		ncclResult_t _r = (call);                                                                                    \
-		if (_r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+		if (_r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(_r)); \
 	} while (0)
 
 extern "C" int admmb_dist_unique_id(char *out128) {
 	if (!out128) return ADMMB_E_ARG;
+	if (!nccl_load()) return ADMMB_E_CUDA;
 	ncclUniqueId id;
-	if (ncclGetUniqueId(&id) != ncclSuccess) return ADMMB_E_CUDA;
+	if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ADMMB_E_CUDA;
 	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
 	memcpy(out128, &id, sizeof(id));
 	return ADMMB_OK;
@@ -40,10 +74,11 @@ extern "C" int admmb_dist_init(admmb_ctx *ctx, int rank, int world, const char *
 	ctx->dist_rank = rank;
 	ctx->dist_world = world;
 	if (world == 1) return ADMMB_OK;
+	if (!nccl_load()) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "libnccl.so.2 could not be loaded: %s", dlerror());
 	ncclUniqueId id;
 	memcpy(&id, id128, sizeof(id));
 	ncclComm_t comm;
-	ADMMB_NCCL(ctx, ncclCommInitRank(&comm, world, id, rank));
+	ADMMB_NCCL(ctx, g_nccl.CommInitRank(&comm, world, id, rank));
 	ctx->nccl_comm = (void *)comm;
 	return ADMMB_OK;
 }
@@ -53,18 +88,18 @@ namespace admmb {
 int dist_allgather_nodes(admmb_ctx *ctx, double *vec) {
 	if (ctx->dist_world == 1) return ADMMB_OK;
 	const size_t cnt = 3 * (size_t)ctx->chunk;
-	ADMMB_NCCL(ctx, ncclAllGather(vec + cnt * ctx->dist_rank, vec, cnt, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	ADMMB_NCCL(ctx, g_nccl.AllGather(vec + cnt * ctx->dist_rank, vec, cnt, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 	return ADMMB_OK;
 }
 
 int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count) {
 	if (ctx->dist_world == 1) return ADMMB_OK;
-	ADMMB_NCCL(ctx, ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	ADMMB_NCCL(ctx, g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 	return ADMMB_OK;
 }
 
 void dist_destroy(admmb_ctx *ctx) {
-	if (ctx->nccl_comm) ncclCommDestroy((ncclComm_t)ctx->nccl_comm);
+	if (ctx->nccl_comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
 	ctx->nccl_comm = nullptr;
 }
 
