@@ -139,13 +139,12 @@ def test_local_step_replay_on_cpu(name):
                 exact = np.array_equal(z, gz) and np.array_equal(u, gu)
                 n_total += 1
                 n_exact += int(exact)
-                # triangle forces: own 3x2 SVD, gauge-free result -> agreement to rounding (absolute, u can be ~0)
                 worst = max(worst, float(np.abs(z - gz).max()), float(np.abs(u - gu).max()))
-                if cb.type != 1:
-                    assert exact, f"{name}: batch {i} ({cb.b['type']}) frame {f} it {k} not bit-exact: z {rel_l2(z, gz):.2e} u {rel_l2(u, gu):.2e}"
+                # every force class -- triangles included, through the restated Eigen 3x2 JacobiSVD -- is bit-exact
+                assert exact, f"{name}: batch {i} ({cb.b['type']}) frame {f} it {k} not bit-exact: z {rel_l2(z, gz):.2e} u {rel_l2(u, gu):.2e}"
             if hyper:
                 got = np.concatenate([cb.state for cb in hyper])
                 assert np.array_equal(got, gold["prox_it"][f, k]), f"{name}: L-BFGS state differs at frame {f} it {k}"
             u_prev = gold["u_it"][f, k]
     print(f"{name}: {n_exact}/{n_total} batch projections bit-exact, worst abs difference {worst:.2e}")
-    assert worst <= 1e-12
+    assert worst == 0.0 and n_exact == n_total

@@ -94,18 +94,14 @@ def test_iteration_teacher_forced(name):
           f"global step worst rel-L2 of x {worst_x:.2e}")
     assert worst_local <= TOL_ITER
     assert worst_x <= TOL_ITER
-    # Bit-exactness: tets (ARAP, volume, StVK, and NeoHookean through the glibc log clone), springs, hinges, anchors
-    # and collisions restate the reference's arithmetic literally.  Triangle forces use our own 3x2 SVD (the
-    # reference's goes through Eigen's column-pivoting Householder QR); their outputs are gauge-free, so they agree
-    # to rounding (<= 1e-12) but not to the last bit.
-    has_tris = any(b["type"] == "tris" for b in scenario["scene"]["batches"])
+    # Bit-exactness: tets (ARAP, volume, StVK, and NeoHookean through the glibc log clone), triangles (through the
+    # restated Eigen 3x2 JacobiSVD: column-pivoting Householder QR + 2x2 Jacobi), springs, hinges, anchors and
+    # collisions restate the reference's arithmetic literally.
     has_fung = any(b["type"] == "tris" and int(b["kind"]) == 2 for b in scenario["scene"]["batches"])
     if has_fung:
         # FungTriangle: exp() of the device libm differs from glibc's in the last bit and the truncated L-BFGS
         # amplifies it (measured 7e-12); the 1e-9 gate above applies
         pass
-    elif has_tris:
-        assert worst_local <= 1e-12
     else:
         assert n_exact == n_total, f"{name}: {n_total - n_exact} of {n_total} local-step vectors differ in the last bits"
 
