@@ -48,6 +48,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	for (Batch &b : ctx->batches) free_batch(b);
+	for (ExplicitEntry &e : ctx->explicit_forces) { e.d_idx.free(); e.d_level_ptr.free(); }
 	ctx->d_x.free(); ctx->d_v.free(); ctx->d_xbar.free(); ctx->d_Mxbar.free(); ctx->d_currx.free(); ctx->d_b.free(); ctx->d_m.free();
 	ctx->d_io.free(); ctx->d_node_perm.free(); ctx->d_P.free(); ctx->d_vert_ptr.free(); ctx->d_vert_slots.free();
 	drop_iteration_graph(ctx);
@@ -175,17 +176,47 @@ extern "C" int admmb_add_collision(admmb_ctx *ctx, int nshapes, const int *shape
 	return id;
 }
 
+// ---- explicit forces (System::explicit_forces, applied in registration order at the start of every frame) ----
+static int add_explicit(admmb_ctx *ctx, int kind, int count, const int *idx, int per, const double *dir3, const char *what) {
+	CHECK_BUILDING(ctx);
+	if (!dir3) ADMMB_FAIL(ctx, ADMMB_E_ARG, "%s: null direction", what);
+	if (count < 0 || (count > 0 && !idx)) ADMMB_FAIL(ctx, ADMMB_E_ARG, "%s: bad count / null indices", what);
+	if (ctx->n == 0) ADMMB_FAIL(ctx, ADMMB_E_STATE, "%s: call admmb_set_nodes first", what);
+	for (long i = 0; i < (long)count * per; ++i)
+		if (idx[i] < 0 || idx[i] >= ctx->n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "%s: node index %d out of range", what, idx[i]);
+	ExplicitEntry e;
+	e.kind = kind;
+	e.count = count;
+	for (int j = 0; j < 3; ++j) e.dir[j] = dir3[j];
+	if (count) e.idx.assign(idx, idx + (size_t)count * per);
+	ctx->explicit_forces.push_back(e);
+	return (int)ctx->explicit_forces.size() - 1;
+}
+
 extern "C" int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3) {
 	CHECK_CTX(ctx);
 	if (!dir3) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null direction");
 	if (id < 0) {
-		if (ctx->gravity.size() >= 24) ADMMB_FAIL(ctx, ADMMB_E_ARG, "at most 8 device-side explicit forces");
-		ctx->gravity.insert(ctx->gravity.end(), dir3, dir3 + 3);
-		return (int)(ctx->gravity.size() / 3) - 1;
+		// a plain ExplicitForce over all nodes may also be added after finalize (it needs no device data)
+		ExplicitEntry e;
+		for (int j = 0; j < 3; ++j) e.dir[j] = dir3[j];
+		ctx->explicit_forces.push_back(e);
+		return (int)ctx->explicit_forces.size() - 1;
 	}
-	if ((size_t)id >= ctx->gravity.size() / 3) ADMMB_FAIL(ctx, ADMMB_E_ARG, "unknown explicit force id %d", id);
-	for (int j = 0; j < 3; ++j) ctx->gravity[3 * id + j] = dir3[j];
+	if ((size_t)id >= ctx->explicit_forces.size()) ADMMB_FAIL(ctx, ADMMB_E_ARG, "unknown explicit force id %d", id);
+	for (int j = 0; j < 3; ++j) ctx->explicit_forces[id].dir[j] = dir3[j];
 	return id;
+}
+
+extern "C" int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *idx, const double *dir3) {
+	if (!ctx) return ADMMB_E_ARG;
+	if (count < 1) { CHECK_CTX(ctx); ADMMB_FAIL(ctx, ADMMB_E_ARG, "explicit subset: need count >= 1 (an empty index list means ALL nodes in the reference: use admmb_set_gravity)"); }
+	return add_explicit(ctx, 1, count, idx, 1, dir3, "explicit subset");
+}
+
+extern "C" int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3) {
+	if (!ctx) return ADMMB_E_ARG;
+	return add_explicit(ctx, 2, ntris, tris3, 3, dir3, "wind");
 }
 
 extern "C" int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters) {
@@ -359,6 +390,10 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		ADMMB_CUDA(ctx, ctx->d_io.alloc(6 * (size_t)n));
 		ADMMB_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, 6 * (size_t)n * sizeof(double)));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
+	}
+	for (ExplicitEntry &e : ctx->explicit_forces) {
+		int rc = upload_explicit(ctx, e);
+		if (rc) return rc;
 	}
 	int rc = setup_solver(ctx);
 	if (rc) return rc;

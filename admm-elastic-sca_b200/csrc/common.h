@@ -82,6 +82,17 @@ struct Batch {
 	DevBuf<double> d_shape_params;
 };
 
+// Explicit forces applied on the device at the start of every frame, in registration order (System.cpp:37-39).
+struct ExplicitEntry {
+	int kind = 0;                 // 0 ExplicitForce over all nodes, 1 ExplicitForce over a node subset, 2 WindForce
+	double dir[3] = { 0, 0, 0 };
+	std::vector<int> idx;         // kind 1: user node ids; kind 2: 3 user node ids per triangle, reference order
+	int count = 0;                // nodes / triangles
+	// device: kind 1 internal node ids; kind 2 triangles regrouped into dependency wavefronts, [3][count] internal ids
+	DevBuf<int> d_idx, d_level_ptr;
+	int n_levels = 0;             // kind 2: wavefronts; kind 1: distinct nodes
+};
+
 struct DirectSolver; // direct_solve.cu
 struct PcgSolver;    // kernels_global.cu
 
@@ -110,7 +121,7 @@ struct admmb_ctx {
 	std::vector<int> node_perm;  // internal -> user
 	std::vector<int> node_iperm; // user -> internal
 	std::vector<admmb::Batch> batches;
-	std::vector<double> gravity; // 3 per registered ExplicitForce
+	std::vector<admmb::ExplicitEntry> explicit_forces;
 
 	int solver = ADMMB_SOLVER_DIRECT;
 	double cg_tol = 1e-12;
@@ -171,6 +182,9 @@ struct admmb_ctx {
 namespace admmb {
 // rest_state.cpp
 int compute_rest_state(admmb_ctx *ctx, Batch &b);
+// Serial WindForce loop -> dependency wavefronts: order[level_ptr[l] .. level_ptr[l+1]) are the triangles of level l (no
+// two of them share a node); triangle t is placed one level after the latest earlier triangle on any of its nodes.
+void wind_wavefronts(int n, int ntris, const int *tris3, std::vector<int> &level_ptr, std::vector<int> &order);
 // ordering.cpp
 void compute_node_order(int n, const double *x3n, const std::vector<int> &adj_ptr, const std::vector<int> &adj_idx,
                         int leaf_size, std::vector<int> &perm /*internal->user*/, std::vector<int> &sep_tree);
@@ -180,6 +194,8 @@ void assemble_system(admmb_ctx *ctx);
 void build_node_graph(const admmb_ctx *ctx, std::vector<int> &ptr, std::vector<int> &idx);
 // kernels_local.cu
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2);
+int launch_explicit(admmb_ctx *ctx, ExplicitEntry &e); // subset ExplicitForce / WindForce on d_x, d_v
+int upload_explicit(admmb_ctx *ctx, ExplicitEntry &e); // after the node order is known
 // kernels_global.cu
 int launch_frame_begin(admmb_ctx *ctx);
 int launch_frame_end(admmb_ctx *ctx);

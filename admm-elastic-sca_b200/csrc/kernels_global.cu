@@ -49,9 +49,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_frame_begin(int n3, double dt, 
 	if (t >= n3) return;
 	const int i = t / 3, j = t - 3 * i;
 	double vv = v[t];
-	for (int g = 0; g < G.count; ++g) vv += (dt * G.g[g][j]);
+	// __dmul_rn / __dadd_rn: never contracted into an FMA -- the reference rounds the product first (x86-64, no FMA)
+	for (int g = 0; g < G.count; ++g) vv = __dadd_rn(vv, __dmul_rn(dt, G.g[g][j]));
 	v[t] = vv;
-	const double xb = x[t] + dt * vv;
+	const double xb = __dadd_rn(x[t], __dmul_rn(dt, vv));
 	xbar[t] = xb;
 	Mxbar[t] = m[i] * xb;
 	currx[t] = xb;
@@ -69,10 +70,22 @@ __global__ void __launch_bounds__(VEC_THREADS) k_frame_end(int n3, double inv_dt
 int launch_frame_begin(admmb_ctx *ctx) {
 	const int n3 = 3 * ctx->n;
 	GravityList G;
-	G.count = (int)(ctx->gravity.size() / 3);
-	if (G.count > 8) ADMMB_FAIL(ctx, ADMMB_E_ARG, "at most 8 device-side explicit forces");
-	for (int g = 0; g < G.count; ++g)
-		for (int j = 0; j < 3; ++j) G.g[g][j] = ctx->gravity[3 * g + j];
+	G.count = 0;
+	// Explicit forces run in registration order (System.cpp:37-39).  The common case -- a few plain ExplicitForces --
+	// is folded into the frame kernel; anything else (node subsets, wind) gets its own launch, in order.
+	bool plain = ctx->explicit_forces.size() <= 8;
+	for (const ExplicitEntry &e : ctx->explicit_forces) plain = plain && e.kind == 0;
+	if (plain) {
+		for (const ExplicitEntry &e : ctx->explicit_forces) {
+			for (int j = 0; j < 3; ++j) G.g[G.count][j] = e.dir[j];
+			G.count++;
+		}
+	} else {
+		for (ExplicitEntry &e : ctx->explicit_forces) {
+			int rc = launch_explicit(ctx, e);
+			if (rc) return rc;
+		}
+	}
 	k_frame_begin<<<(n3 + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n3, ctx->dt, G, ctx->d_x.p, ctx->d_v.p, ctx->d_m.p,
 	                                                                                   ctx->d_xbar.p, ctx->d_Mxbar.p, ctx->d_currx.p);
 	ctx->launches++;

@@ -113,4 +113,92 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 	return ADMMB_OK;
 }
 
+// ExplicitForce::project (ExplicitForce.cpp:29-39): v += dt * direction, over all nodes or over `indices`.
+__global__ void __launch_bounds__(LOCAL_THREADS) k_explicit_all(int n3, double g0, double g1, double g2, double dt, double *__restrict__ v) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n3) return;
+	const int j = t % 3;
+	v[t] += (dt * (j == 0 ? g0 : (j == 1 ? g1 : g2)));
+}
+// idx holds each listed node once, followed (second half) by how often the caller listed it: a node listed k times
+// receives the increment k times, one rounding each, as in the reference's loop.
+__global__ void __launch_bounds__(LOCAL_THREADS) k_explicit_subset(int count, const int *__restrict__ idx, double g0, double g1, double g2,
+                                                                   double dt, double *__restrict__ v) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count) return;
+	double *vv = v + 3 * (size_t)idx[t];
+	for (int k = idx[count + t]; k > 0; --k) { vv[0] += (dt * g0); vv[1] += (dt * g1); vv[2] += (dt * g2); }
+}
+
+// ---- explicit forces that need their own launch (frame begin) -------------------------------------------
+// WindForce::project (ExplicitForce.cpp:42-98) with the semantics of the reference run on one thread: triangle t reads
+// the velocities already updated by every earlier triangle that shares a node with it.  That dependency chain is
+// resolved at upload time into wavefronts (level(t) = 1 + max level of the earlier triangles on its three nodes), so
+// one CTA walks the levels with a barrier in between and the triangles of a level run in parallel -- same values,
+// same order of additions per node, bit for bit.  (The reference's OpenMP version races on v; this is its serial meaning.)
+#define WIND_THREADS 1024
+__global__ void __launch_bounds__(WIND_THREADS) k_wind(int n_levels, const int *__restrict__ level_ptr, const int *__restrict__ tri, int count,
+                                                       double d0, double d1, double d2, double dt, const double *__restrict__ x, double *v) {
+	const double dir[3] = { d0, d1, d2 };
+	for (int l = 0; l < n_levels; ++l) {
+		const int t1 = level_ptr[l + 1];
+		for (int t = level_ptr[l] + threadIdx.x; t < t1; t += WIND_THREADS) {
+			const size_t a = 3 * (size_t)tri[t], b = 3 * (size_t)tri[count + t], c = 3 * (size_t)tri[2 * count + t];
+			double f[3];
+			wind_triangle(x + a, x + b, x + c, v + a, v + b, v + c, dir, dt, f);
+			// v[idx[j]] += force for j = 0, 1, 2 in corner order: a corner listed twice receives the force twice
+			v[a] += f[0]; v[a + 1] += f[1]; v[a + 2] += f[2];
+			v[b] += f[0]; v[b + 1] += f[1]; v[b + 2] += f[2];
+			v[c] += f[0]; v[c + 1] += f[1]; v[c + 2] += f[2];
+		}
+		__syncthreads();
+	}
+}
+
+int upload_explicit(admmb_ctx *ctx, ExplicitEntry &e) {
+	cudaStream_t s = ctx->stream;
+	if (e.kind == 0 || e.count == 0) return ADMMB_OK;
+	if (e.kind == 1) {
+		std::vector<int> mult(ctx->n, 0), nodes;
+		for (size_t i = 0; i < e.idx.size(); ++i)
+			if (mult[e.idx[i]]++ == 0) nodes.push_back(e.idx[i]);
+		e.n_levels = (int)nodes.size(); // unique nodes
+		std::vector<int> ii(2 * nodes.size());
+		for (size_t i = 0; i < nodes.size(); ++i) { ii[i] = ctx->node_iperm[nodes[i]]; ii[nodes.size() + i] = mult[nodes[i]]; }
+		ADMMB_CUDA(ctx, e.d_idx.upload(ii, s));
+		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
+		return ADMMB_OK;
+	}
+	// wind: wavefront levels of the serial dependency chain, triangles stably regrouped by level
+	const int T = e.count;
+	std::vector<int> ptr, order;
+	wind_wavefronts(ctx->n, T, e.idx.data(), ptr, order);
+	const int depth = (int)ptr.size() - 1;
+	std::vector<int> tri(3 * (size_t)T);
+	for (int p = 0; p < T; ++p)
+		for (int c = 0; c < 3; ++c) tri[(size_t)c * T + p] = ctx->node_iperm[e.idx[3 * (size_t)order[p] + c]];
+	e.n_levels = depth;
+	ADMMB_CUDA(ctx, e.d_idx.upload(tri, s));
+	ADMMB_CUDA(ctx, e.d_level_ptr.upload(ptr, s));
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
+	return ADMMB_OK;
+}
+
+int launch_explicit(admmb_ctx *ctx, ExplicitEntry &e) {
+	cudaStream_t s = ctx->stream;
+	if (e.kind == 0) {
+		const int n = ctx->n;
+		k_explicit_all<<<(3 * n + LOCAL_THREADS - 1) / LOCAL_THREADS, LOCAL_THREADS, 0, s>>>(3 * n, e.dir[0], e.dir[1], e.dir[2], ctx->dt, ctx->d_v.p);
+	} else if (e.kind == 1) {
+		if (e.count == 0) return ADMMB_OK;
+		k_explicit_subset<<<(e.n_levels + LOCAL_THREADS - 1) / LOCAL_THREADS, LOCAL_THREADS, 0, s>>>(e.n_levels, e.d_idx.p, e.dir[0], e.dir[1], e.dir[2], ctx->dt, ctx->d_v.p);
+	} else {
+		if (e.count == 0) return ADMMB_OK;
+		k_wind<<<1, WIND_THREADS, 0, s>>>(e.n_levels, e.d_level_ptr.p, e.d_idx.p, e.count, e.dir[0], e.dir[1], e.dir[2], ctx->dt, ctx->d_x.p, ctx->d_v.p);
+	}
+	ctx->launches++;
+	ADMMB_CUDA(ctx, cudaGetLastError());
+	return ADMMB_OK;
+}
+
 } // namespace admmb

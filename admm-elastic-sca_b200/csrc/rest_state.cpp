@@ -188,4 +188,22 @@ int compute_rest_state(admmb_ctx *ctx, Batch &b) {
 	return ADMMB_OK;
 }
 
+void wind_wavefronts(int n, int ntris, const int *tris3, std::vector<int> &level_ptr, std::vector<int> &order) {
+	std::vector<int> node_level(n, 0), level(ntris);
+	int depth = 0;
+	for (int t = 0; t < ntris; ++t) {
+		int l = 0;
+		for (int c = 0; c < 3; ++c) l = std::max(l, node_level[tris3[3 * (size_t)t + c]]);
+		level[t] = l;
+		for (int c = 0; c < 3; ++c) node_level[tris3[3 * (size_t)t + c]] = l + 1;
+		depth = std::max(depth, l + 1);
+	}
+	level_ptr.assign(depth + 1, 0);
+	for (int t = 0; t < ntris; ++t) level_ptr[level[t] + 1]++;
+	for (int l = 0; l < depth; ++l) level_ptr[l + 1] += level_ptr[l];
+	std::vector<int> fill(level_ptr.begin(), level_ptr.end() - 1);
+	order.resize(ntris);
+	for (int t = 0; t < ntris; ++t) order[fill[level[t]]++] = t;
+}
+
 } // namespace admmb

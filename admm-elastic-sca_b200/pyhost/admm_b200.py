@@ -22,7 +22,7 @@ STATE_X, STATE_Z, STATE_U, STATE_PROX, STATE_PROX_ITERS = 0, 1, 2, 3, 4
 EXPORTS = [
     "admmb_create", "admmb_destroy", "admmb_last_error", "admmb_version", "admmb_set_nodes", "admmb_add_tets",
     "admmb_add_tris", "admmb_add_springs", "admmb_add_bends", "admmb_add_static_anchors", "admmb_add_moving_anchors",
-    "admmb_add_collision", "admmb_set_gravity", "admmb_set_solver", "admmb_finalize", "admmb_step",
+    "admmb_add_collision", "admmb_set_gravity", "admmb_add_explicit_subset", "admmb_add_wind", "admmb_set_solver", "admmb_finalize", "admmb_step",
     "admmb_step_dump", "admmb_debug_local_step", "admmb_debug_global_step", "admmb_step_resident", "admmb_upload_xv", "admmb_download_xv", "admmb_update_anchor_targets",
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
@@ -62,6 +62,8 @@ def lib():
     L.admmb_add_moving_anchors.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_add_collision.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_set_gravity.argtypes = [vp, C.c_int, _dp]
+    L.admmb_add_explicit_subset.argtypes = [vp, C.c_int, _ip, _dp]
+    L.admmb_add_wind.argtypes = [vp, C.c_int, _ip, _dp]
     L.admmb_set_solver.argtypes = [vp, C.c_int, C.c_double, C.c_int]
     L.admmb_finalize.argtypes = [vp, C.c_double]
     L.admmb_step.argtypes = [vp, C.c_int, _dp, _dp]
@@ -109,7 +111,7 @@ class System:
     recompute_weights().  Built from a scene dictionary (scenes.py).
     """
 
-    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None):
+    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None, host_explicit=False):
         """dist = (rank, world, id128 bytes) partitions the mesh over `world` processes (PCG only)."""
         L = lib()
         self.L = L
@@ -157,19 +159,29 @@ class System:
             if bid < 0:
                 self._ck(bid)
             self.batch_ids.append(bid)
-        # Explicit forces run in list order (System.cpp:37-39).  Gravity-only scenes keep them on the device;
-        # as soon as a host-side one (wind) is present, all of them are applied by the caller, in order.
+        # Explicit forces run in list order (System.cpp:37-39), on the device: gravity (all nodes or a subset) and
+        # wind.  host_explicit=True keeps them on the host instead (what a user-defined ExplicitForce subclass gets:
+        # the caller applies them to m_v before step(), see apply_host_explicit) -- used by the tests as a cross-check.
         self.gravity_ids = []
         self.host_explicit = []
         ex = scene.get("explicit", [])
-        if all(e["type"] == "gravity" for e in ex):
+        if host_explicit:
+            self.host_explicit = list(ex)
+        else:
             for e in ex:
-                gid = L.admmb_set_gravity(h, -1, _f64(e["dir"]))
+                if e["type"] == "gravity" and e.get("indices") is not None and len(e["indices"]):
+                    ii = _i32(e["indices"])
+                    gid = L.admmb_add_explicit_subset(h, ii.size, ii, _f64(e["dir"]))
+                elif e["type"] == "gravity":
+                    gid = L.admmb_set_gravity(h, -1, _f64(e["dir"]))
+                elif e["type"] == "wind":
+                    tt = _i32(e["tris"])
+                    gid = L.admmb_add_wind(h, tt.size // 3, tt, _f64(e["dir"]))
+                else:
+                    raise ValueError(e["type"])
                 if gid < 0:
                     self._ck(gid)
                 self.gravity_ids.append(gid)
-        else:
-            self.host_explicit = list(ex)
         self._ck(L.admmb_set_solver(h, int(solver), float(cg_tol), int(cg_max_iters)))
         if dist is not None:
             self._ck(L.admmb_dist_init(h, int(dist[0]), int(dist[1]), dist[2]))
@@ -194,7 +206,10 @@ class System:
     def apply_host_explicit(self):
         """ExplicitForce::project / WindForce::project for forces kept on the host (per frame, before step)."""
         for e in self.host_explicit:
-            if e["type"] == "gravity":
+            if e["type"] == "gravity" and e.get("indices") is not None and len(e["indices"]):
+                for i in e["indices"]:
+                    self.m_v.reshape(-1, 3)[int(i)] += self.dt * _f64(e["dir"])
+            elif e["type"] == "gravity":
                 self.m_v.reshape(-1, 3)[:] += self.dt * _f64(e["dir"])
             else:
                 wind_project(self.m_x, self.m_v, e["tris"], e["dir"], self.dt)

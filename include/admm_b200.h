@@ -85,9 +85,18 @@ int admmb_add_moving_anchors(admmb_ctx *ctx, int count, const int *idx, const do
 /* CollisionForce over all nodes (CollisionForce.hpp:28-41); shapes in list order, params4 = {cx,cy,cz,radius}. */
 int admmb_add_collision(admmb_ctx *ctx, int nshapes, const int *shape_kind, const double *params4, double weight);
 
-/* ExplicitForce applied to all nodes at the start of every step (ExplicitForce.cpp:29-39); dir3 may be changed
- * between steps by calling again with the returned id.  id < 0 adds a new one. */
+/* Explicit forces (System::explicit_forces): applied on the device to v at the start of every step, in the order
+ * they were registered (System.cpp:37-39).  Each call returns the force's id.
+ * admmb_set_gravity: ExplicitForce over all nodes (ExplicitForce.cpp:29-39); id < 0 adds a new one (allowed after
+ *   finalize too), id >= 0 changes the direction of ANY registered explicit force (wind included) between steps.
+ * admmb_add_explicit_subset: ExplicitForce restricted to `indices` (ExplicitForce.hpp:54-55).
+ * admmb_add_wind: WindForce (ExplicitForce.hpp:61-68, ExplicitForce.cpp:42-98) over ntris triangles, tris3 = 3 node ids
+ *   each.  Semantics = the reference on ONE OpenMP thread: triangle t sees the velocities already updated by the
+ *   earlier triangles sharing a node with it (its multi-threaded loop races on v); reproduced bit for bit on the device
+ *   by walking the dependency wavefronts.  Subsets and wind must be registered before admmb_finalize. */
 int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3);
+int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *idx, const double *dir3);
+int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3);
 
 /* Solver choice and tolerances; call before admmb_finalize.  tol and max_cg_iters apply to PCG only. */
 int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters);
@@ -107,8 +116,9 @@ int admmb_finalize(admmb_ctx *ctx, double timestep_s);
 
 /* ---- per frame: replaces System::step() (System.cpp:26-75) ------------------------------------ */
 /* x3n_inout / v3n_inout: host System::m_x / m_v, read at entry (callers may have modified them, e.g.
- * singletet.cpp:40) and written at exit.  Explicit forces registered with admmb_set_gravity are applied on
- * the device; any other ExplicitForce must have been applied to v by the caller beforehand. */
+ * singletet.cpp:40) and written at exit.  Explicit forces registered with admmb_set_gravity / admmb_add_explicit_subset /
+ * admmb_add_wind are applied on the device; any other (user-defined) ExplicitForce must have been applied to v by the
+ * caller beforehand. */
 int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout);
 
 /* Diagnostic variant of admmb_step for parity dumps: additionally copies, for every ADMM iteration it,

@@ -19,25 +19,37 @@ import scenes  # noqa: E402
 from scenarios import RefAdapter, build_scenarios, run_scenario  # noqa: E402
 
 
+# The reference's own sensitivity: the same run from initial positions perturbed by 1e-15, for SENS_SEEDS different
+# sign patterns; the stored value is the MAXIMUM over the seeds.  The response is heavy-tailed (the truncated line search
+# bifurcates: e.g. cube2_stvk answers 11 of 12 perturbations with 5e-8 and one with 6e-6), so a single sample
+# under-states what a 1-ulp difference can do.
+SENS_SEEDS = tuple(range(99, 99 + 16))
+
+
+def sensitivity(sc, res, keys):
+    out = {"sens_" + k: 0.0 for k in keys}
+    for seed in SENS_SEEDS:
+        ad = RefAdapter(sc["scene"])
+        per = run_scenario(ad, sc, dump=True, perturb=1e-15, seed=seed)
+        ad.close()
+        for key in keys:
+            a, g = per[key], res[key]
+            if a.size == 0:
+                continue
+            flat = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
+            num = np.linalg.norm(flat[0] - flat[1], axis=1)
+            den = np.linalg.norm(flat[1], axis=1)
+            out["sens_" + key] = max(out["sens_" + key], float(np.max(np.where(den > 0, num / np.where(den > 0, den, 1.0), num))))
+    return {k: np.float64(v) for k, v in out.items()}
+
+
 def main():
     S = build_scenarios()
     for name, sc in S.items():
         ad = RefAdapter(sc["scene"])
         res = run_scenario(ad, sc, dump=True)
         ad.close()
-        # the reference's own sensitivity: same run from initial positions perturbed by 1e-15 (relative)
-        ad = RefAdapter(sc["scene"])
-        per = run_scenario(ad, sc, dump=True, perturb=1e-15)
-        ad.close()
-        for key in ("x_it", "z_it", "u_it", "x", "v"):
-            a, g = per[key], res[key]
-            if a.size == 0:
-                res["sens_" + key] = np.float64(0.0)
-                continue
-            flat = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
-            num = np.linalg.norm(flat[0] - flat[1], axis=1)
-            den = np.linalg.norm(flat[1], axis=1)
-            res["sens_" + key] = np.float64(np.max(np.where(den > 0, num / np.where(den > 0, den, 1.0), num)))
+        res.update(sensitivity(sc, res, ("x_it", "z_it", "u_it", "x", "v")))
         scenes.save_scene(os.path.join(HERE, f"{name}.scene.npz"), sc["scene"])
         np.savez_compressed(os.path.join(HERE, f"{name}.ref.npz"), **res)
         sz = os.path.getsize(os.path.join(HERE, f"{name}.ref.npz")) / 1024
@@ -63,14 +75,8 @@ def shipped():
         ad = RefAdapter(sc["scene"])
         res = run_scenario(ad, sc, dump=True)
         ad.close()
-        ad = RefAdapter(sc["scene"])
-        per = run_scenario(ad, sc, dump=True, perturb=1e-15)
-        ad.close()
         out = dict(x_it=res["x_it"][:1], x=res["x"], v=res["v"][-1:])   # z/u dumps of these scenes are too large to commit
-        for key in ("x_it", "x"):
-            a, g = per[key], res[key]
-            flat = a.reshape(-1, a.shape[-1]), g.reshape(-1, g.shape[-1])
-            out["sens_" + key] = np.float64(np.max(np.linalg.norm(flat[0] - flat[1], axis=1) / np.linalg.norm(flat[1], axis=1)))
+        out.update(sensitivity(sc, res, ("x_it", "x")))
         np.savez_compressed(os.path.join(HERE, f"shipped_{name}.ref.npz"), **out)
         print(f"shipped {name:12s} frames={sc['frames']} nodes={sc['scene']['x'].shape[0]} rows={res['z_it'].shape[2]} "
               f"self-sensitivity x_it {out['sens_x_it']:.1e} x {out['sens_x']:.1e}")

@@ -93,3 +93,24 @@ extern "C" int hc_batch_local(int type, int kind, int n, const double *x_rest, i
 			for (int e = 0; e < count; ++e) anchor_pos_out[(size_t)e * 3 + k] = aux[(size_t)k * count + e];
 	return 0;
 }
+
+// WindForce::project through the product's wavefront schedule (csrc/rest_state.cpp wind_wavefronts + elastic_math.h
+// wind_triangle), levels walked in order and the triangles of a level in REVERSE order -- any order inside a level must
+// give the serial loop's result.  serial != 0 walks the triangle list as given instead.
+extern "C" int hc_wind(int n, int ntris, const int *tris3, const double *dir, double dt, const double *x, double *v, int serial) {
+	std::vector<int> ptr, order;
+	if (serial) { ptr = { 0, ntris }; order.resize(ntris); for (int t = 0; t < ntris; ++t) order[t] = t; }
+	else admmb::wind_wavefronts(n, ntris, tris3, ptr, order);
+	for (size_t l = 0; l + 1 < ptr.size(); ++l) {
+		const int lo = ptr[l], hi = ptr[l + 1];
+		for (int q = 0; q < hi - lo; ++q) {
+			const int t = order[serial ? lo + q : hi - 1 - q];
+			const size_t a = 3 * (size_t)tris3[3 * t], b = 3 * (size_t)tris3[3 * t + 1], c = 3 * (size_t)tris3[3 * t + 2];
+			double f[3];
+			admmb::wind_triangle(x + a, x + b, x + c, v + a, v + b, v + c, dir, dt, f);
+			const size_t ids[3] = { a, b, c };
+			for (int k = 0; k < 3; ++k) { v[ids[k]] += f[0]; v[ids[k] + 1] += f[1]; v[ids[k] + 2] += f[2]; }
+		}
+	}
+	return (int)ptr.size() - 1;
+}

@@ -104,7 +104,7 @@ class DevAdapter:
         self.sim.close()
 
 
-def run_scenario(adapter, scenario, dump=True, perturb=None):
+def run_scenario(adapter, scenario, dump=True, perturb=None, seed=99):
     """Runs `frames` steps; returns dict of stacked per-frame arrays.  perturb = relative size of a random
     +-perturbation of the initial positions (used to measure the reference's own sensitivity)."""
     sc = scenario["scene"]
@@ -112,7 +112,7 @@ def run_scenario(adapter, scenario, dump=True, perturb=None):
     if perturb:
         # relative AND absolute (a planar cloth has z == 0 everywhere: a purely relative perturbation would leave the
         # out-of-plane direction, the one the wind excites, untouched)
-        rng = np.random.default_rng(99)
+        rng = np.random.default_rng(seed)
         sgn = rng.choice([-1.0, 1.0], size=x0.shape)
         x0 = x0 * (1.0 + perturb * sgn) + perturb * np.abs(x0).max() * rng.choice([-1.0, 1.0], size=x0.shape)
     if "x_after_init" in sc or perturb:
