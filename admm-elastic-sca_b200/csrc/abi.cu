@@ -57,6 +57,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	dist_destroy(ctx);
 	for (cudaEvent_t ev : ctx->timing.ev) cudaEventDestroy(ev);
 	for (int k = 0; k < 2; ++k) if (ctx->ev_region[k]) cudaEventDestroy(ctx->ev_region[k]);
+	for (const auto &r : ctx->host_regs) cudaHostUnregister(r.first);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -539,20 +540,62 @@ static int collect_timing(admmb_ctx *ctx, int admm_iters, cudaEvent_t e_begin, c
 	return ADMMB_OK;
 }
 
+// Host copies between the caller's (pageable) buffers and the pinned staging area are the largest host-side cost of
+// admmb_step at 1 M tets (4 x 4.2 MB per frame at single-thread memcpy speed): split them over a few OpenMP threads.
+static void staged_copy(void *dst, const void *src, size_t bytes) {
+	const size_t chunk = (size_t)1 << 18;
+	if (bytes < 4 * chunk) { memcpy(dst, src, bytes); return; }
+	const long nchunks = (long)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) num_threads(8)
+	for (long c = 0; c < nchunks; ++c) {
+		const size_t o = (size_t)c * chunk;
+		memcpy((char *)dst + o, (const char *)src + o, std::min(chunk, bytes - o));
+	}
+}
+
+static bool is_registered(const admmb_ctx *ctx, const void *p, size_t bytes) {
+	for (const auto &r : ctx->host_regs)
+		if ((const char *)p >= r.first && (const char *)p + bytes <= r.first + r.second) return true;
+	return false;
+}
+
+extern "C" int admmb_register_host_buffer(admmb_ctx *ctx, void *ptr, long bytes) {
+	CHECK_CTX(ctx);
+	if (!ptr || bytes <= 0) ADMMB_FAIL(ctx, ADMMB_E_ARG, "register_host_buffer: null pointer / empty range");
+	if (is_registered(ctx, ptr, (size_t)bytes)) return ADMMB_OK;
+	ADMMB_CUDA(ctx, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+	ctx->host_regs.push_back(std::make_pair((char *)ptr, (size_t)bytes));
+	return ADMMB_OK;
+}
+
+extern "C" int admmb_unregister_host_buffer(admmb_ctx *ctx, void *ptr) {
+	CHECK_CTX(ctx);
+	for (size_t i = 0; i < ctx->host_regs.size(); ++i)
+		if (ctx->host_regs[i].first == (char *)ptr) {
+			if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+			cudaError_t e = cudaHostUnregister(ptr);
+			ctx->host_regs.erase(ctx->host_regs.begin() + i);
+			ADMMB_CUDA(ctx, e);
+			return ADMMB_OK;
+		}
+	ADMMB_FAIL(ctx, ADMMB_E_ARG, "unregister_host_buffer: %p was not registered", ptr);
+}
+
 extern "C" int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n) {
 	CHECK_READY(ctx);
 	const size_t n3 = 3 * (size_t)ctx->n;
 	cudaStream_t s = ctx->stream;
-	if (x3n) {
-		memcpy(ctx->h_pin, x3n, n3 * sizeof(double));
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p, ctx->h_pin, n3 * sizeof(double), cudaMemcpyHostToDevice, s));
-		int rc = launch_permute_in(ctx, ctx->d_io.p, ctx->d_x.p);
-		if (rc) return rc;
-	}
-	if (v3n) {
-		memcpy(ctx->h_pin + n3, v3n, n3 * sizeof(double));
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p + n3, ctx->h_pin + n3, n3 * sizeof(double), cudaMemcpyHostToDevice, s));
-		int rc = launch_permute_in(ctx, ctx->d_io.p + n3, ctx->d_v.p);
+	const double *src[2] = { x3n, v3n };
+	double *dst[2] = { ctx->d_x.p, ctx->d_v.p };
+	for (int k = 0; k < 2; ++k) {
+		if (!src[k]) continue;
+		const double *from = src[k];
+		if (!is_registered(ctx, from, n3 * sizeof(double))) {
+			staged_copy(ctx->h_pin + k * n3, from, n3 * sizeof(double));
+			from = ctx->h_pin + k * n3;
+		}
+		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p + k * n3, from, n3 * sizeof(double), cudaMemcpyHostToDevice, s));
+		int rc = launch_permute_in(ctx, ctx->d_io.p + k * n3, dst[k]);
 		if (rc) return rc;
 	}
 	return ADMMB_OK;
@@ -562,19 +605,20 @@ extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
 	CHECK_READY(ctx);
 	const size_t n3 = 3 * (size_t)ctx->n;
 	cudaStream_t s = ctx->stream;
-	if (x3n) {
-		int rc = launch_permute_out(ctx, ctx->d_x.p, ctx->d_io.p);
+	double *out[2] = { x3n, v3n };
+	const double *src[2] = { ctx->d_x.p, ctx->d_v.p };
+	bool staged[2] = { false, false };
+	for (int k = 0; k < 2; ++k) {
+		if (!out[k]) continue;
+		int rc = launch_permute_out(ctx, src[k], ctx->d_io.p + k * n3);
 		if (rc) return rc;
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->d_io.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-	}
-	if (v3n) {
-		int rc = launch_permute_out(ctx, ctx->d_v.p, ctx->d_io.p + n3);
-		if (rc) return rc;
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + n3, ctx->d_io.p + n3, n3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+		staged[k] = !is_registered(ctx, out[k], n3 * sizeof(double));
+		ADMMB_CUDA(ctx, cudaMemcpyAsync(staged[k] ? ctx->h_pin + k * n3 : out[k], ctx->d_io.p + k * n3, n3 * sizeof(double),
+		                                cudaMemcpyDeviceToHost, s));
 	}
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
-	if (x3n) memcpy(x3n, ctx->h_pin, n3 * sizeof(double));
-	if (v3n) memcpy(v3n, ctx->h_pin + n3, n3 * sizeof(double));
+	for (int k = 0; k < 2; ++k)
+		if (out[k] && staged[k]) staged_copy(out[k], ctx->h_pin + k * n3, n3 * sizeof(double));
 	return ADMMB_OK;
 }
 

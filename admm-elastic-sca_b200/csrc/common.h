@@ -138,6 +138,7 @@ struct admmb_ctx {
 
 	// pinned host staging
 	double *h_pin = nullptr;
+	std::vector<std::pair<char *, size_t>> host_regs; // caller buffers page-locked by admmb_register_host_buffer
 
 	// scalar system matrix (host CSR, internal order, full symmetric pattern)
 	std::vector<int> A_ptr, A_idx;

@@ -27,6 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer",
 ]
 
 
@@ -62,6 +63,8 @@ def lib():
     L.admmb_add_moving_anchors.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_add_collision.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_set_gravity.argtypes = [vp, C.c_int, _dp]
+    L.admmb_register_host_buffer.argtypes = [vp, vp, C.c_long]
+    L.admmb_unregister_host_buffer.argtypes = [vp, vp]
     L.admmb_add_explicit_subset.argtypes = [vp, C.c_int, _ip, _dp]
     L.admmb_add_wind.argtypes = [vp, C.c_int, _ip, _dp]
     L.admmb_set_solver.argtypes = [vp, C.c_int, C.c_double, C.c_int]
@@ -111,7 +114,7 @@ class System:
     recompute_weights().  Built from a scene dictionary (scenes.py).
     """
 
-    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None, host_explicit=False):
+    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None, host_explicit=False, pin_host=False):
         """dist = (rank, world, id128 bytes) partitions the mesh over `world` processes (PCG only)."""
         L = lib()
         self.L = L
@@ -186,6 +189,13 @@ class System:
         if dist is not None:
             self._ck(L.admmb_dist_init(h, int(dist[0]), int(dist[1]), dist[2]))
         self._ck(L.admmb_finalize(h, self.dt))
+        # pin_host: page-lock m_x / m_v so that step() transfers them directly (no staging copy); the arrays are kept
+        # alive until close() even if the caller rebinds self.m_x
+        self._pinned = []
+        if pin_host:
+            for a in (self.m_x, self.m_v):
+                self._ck(L.admmb_register_host_buffer(h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+                self._pinned.append(a)
 
     def _ck(self, rc):
         if rc < 0:

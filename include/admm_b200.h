@@ -138,6 +138,13 @@ int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames);
 int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n);   /* either may be NULL */
 int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n);             /* either may be NULL */
 
+/* Optional: page-lock a caller-owned host buffer (e.g. the storage of System::m_x / m_v) so that admmb_step /
+ * admmb_upload_xv / admmb_download_xv transfer it directly instead of staging it through the context's own pinned
+ * area.  The buffer must stay allocated until it is unregistered (admmb_destroy unregisters what is left).  Buffers
+ * that are not registered keep working -- they are staged. */
+int admmb_register_host_buffer(admmb_ctx *ctx, void *ptr, long bytes);
+int admmb_unregister_host_buffer(admmb_ctx *ctx, void *ptr);
+
 /* ---- runtime changes ------------------------------------------------------------------------ */
 /* ControlPoint::pos / active of moving-anchor batch `batch` (poordillo.cpp:56,95,199): count entries from `first`.
  * pos3 may be NULL (keep), active may be NULL (keep). */

@@ -93,3 +93,30 @@ def test_state_roundtrip_checkpoint_resume():
     assert err < 1e-3     # not bit-exact: the solve's atomics are unordered and the NH prox is chaotic at this level
     a.close()
     b.close()
+
+
+def test_registered_host_buffers_give_the_same_results():
+    """admmb_register_host_buffer only changes how x / v travel (direct DMA instead of staging), not what is computed;
+    buffers that were never registered -- or other arrays passed later -- keep working."""
+    sc = scenes.cube_scene(3, kind=scenes.TET_ARAP, iters=6)
+    a = admm_b200.System(sc, pin_host=True)
+    b = admm_b200.System(sc, pin_host=False)
+    for s in (a, b):
+        s.set_x(sc["x_after_init"])
+    for _ in range(3):
+        a.step()
+        b.step()
+    assert np.abs(a.m_x - b.m_x).max() <= 1e-12 and np.abs(a.m_v - b.m_v).max() <= 1e-11
+    # an unregistered pair of arrays on the pinned system: staged path
+    x2, v2 = a.m_x.copy(), a.m_v.copy()
+    assert a.L.admmb_step(a.h, 6, x2, v2) == 0
+    b.step()
+    assert np.abs(x2 - b.m_x).max() <= 1e-12
+    # registering twice is a no-op, unregistering an unknown pointer is an argument error
+    p = a.m_x.ctypes.data_as(C.c_void_p)
+    assert a.L.admmb_register_host_buffer(a.h, p, a.m_x.nbytes) == 0
+    assert a.L.admmb_unregister_host_buffer(a.h, x2.ctypes.data_as(C.c_void_p)) == -1
+    assert a.L.admmb_unregister_host_buffer(a.h, p) == 0
+    a.step()   # m_x now staged again, m_v still direct
+    a.close()
+    b.close()
