@@ -309,7 +309,9 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		std::vector<int> gp, gi;
 		build_node_graph(ctx, gp, gi);
 		std::vector<int> blocks;
-		compute_node_order(n, ctx->h_x0.data(), gp, gi, 32, ctx->node_perm, blocks);
+		int leaf = 64; // dissection stops at sub-domains of this many nodes (= the leaf supernodes); ADMMB_ND_LEAF overrides (tuning knob)
+		if (const char *e = getenv("ADMMB_ND_LEAF")) { const int v = atoi(e); if (v >= 8 && v <= 1024) leaf = v; }
+		compute_node_order(n, ctx->h_x0.data(), gp, gi, leaf, ctx->node_perm, blocks);
 		ctx->node_iperm.assign(n, -1);
 		for (int i = 0; i < n; ++i) ctx->node_iperm[ctx->node_perm[i]] = i;
 		direct_set_blocks(ctx, blocks); // dissection blocks = supernode partition of the direct solver

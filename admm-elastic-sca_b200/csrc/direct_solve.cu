@@ -48,8 +48,11 @@ struct DirectSolver {
 	DevBuf<int> d_phase_first, d_phase_count;
 	DevBuf<int> d_err;
 	int n_phases = 0, grid = 0;
-	int mode = 0;   // 0 = launch per level, 1 = persistent bulk-async kernel, 2 = per level with programmatic dependent launch
+	int mode = 3;   // 3 (default) = launch per level, factor columns requested before the vector gather; 0 = launch per level, gather first;
+	                // 1 = persistent bulk-async kernel; 2 = per level with programmatic dependent launch (1, 2: measured slower, kept selectable)
 	int unroll = 16; // loads in flight per thread of the per-level kernel (ADMMB_SOLVE_UNROLL = 8 | 16 | 32)
+	int slots = 0;   // resident CTAs of the per-level kernel on the whole device
+	int split = 0;   // ADMMB_SOLVE_SPLIT: 0 = choose per level, else log2 of the forced column split + 1
 };
 
 // fire-and-forget FP64 add at L2 (RED.E.ADD.F64): the generic atomicAdd would also emit a shared-memory CAS path
@@ -95,6 +98,77 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level(const SolveTile *__restr
 	}
 	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
 	const int go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r;
+	red_add(vout + 3 * (size_t)go + 0, a0);
+	red_add(vout + 3 * (size_t)go + 1, a1);
+	red_add(vout + 3 * (size_t)go + 2, a2);
+}
+
+// Variant (ADMMB_SOLVE_MODE=3): the first UNROLL columns of the tile are requested BEFORE the right-hand-side gather.
+// The factor does not depend on the vectors, so the two latency chains (descriptor -> index -> vector gather, and
+// descriptor -> factor columns) overlap instead of following each other; the small tiles of the lower tree levels are
+// one such chain long, so this is where the time goes there (profiles/r1c_solve.txt: 13 MB levels take 11 us).
+template <int UNROLL>
+__global__ void __launch_bounds__(TILE_R) k_solve_level_pf(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
+                                                           const int *__restrict__ pool, double *vb, double *vy, double *vx, int split_log2) {
+	// split > 1: the columns of a tile are shared by `split` CTAs (levels with fewer tiles than the machine has CTA
+	// slots are latency bound: a CTA walks its columns in rounds of UNROLL loads, so fewer columns = fewer rounds)
+	const SolveTile t = tiles[blockIdx.x >> split_log2];
+	const int part = blockIdx.x & ((1 << split_log2) - 1);
+	const int per = (((t.ncols + (1 << split_log2) - 1) >> split_log2) + 7) & ~7;
+	const int c0 = part * per;
+	const int c1 = min(t.ncols, c0 + per);
+	if (c0 >= c1) return;
+	__shared__ double sv[TILE_C][3];
+	const int r = threadIdx.x;
+	const bool active = r < t.nrows;
+	const int ld = t.nrows;
+	const double *M = data + t.off + (active ? r : 0) + (size_t)c0 * ld;
+	const int nc = c1 - c0;
+	double m[UNROLL];
+#pragma unroll
+	for (int k = 0; k < UNROLL; ++k) m[k] = (active && k < nc) ? __ldcs(M + (size_t)k * ld) : 0.0;
+	int go = 0;
+	if (active) go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r;
+	const int si = (t.flags >> TF_IN_SHIFT) & 3, so = (t.flags >> TF_OUT_SHIFT) & 3;
+	const double *vin = si == 0 ? vb : (si == 1 ? vy : vx);
+	double *vout = so == 0 ? vb : (so == 1 ? vy : vx);
+	for (int c = threadIdx.x; c < TILE_C; c += TILE_R) {
+		if (c < nc) {
+			const int gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c0 + c] : t.in_idx + c0 + c;
+			sv[c][0] = vin[3 * (size_t)gi + 0];
+			sv[c][1] = vin[3 * (size_t)gi + 1];
+			sv[c][2] = vin[3 * (size_t)gi + 2];
+		} else {
+			sv[c][0] = 0.0; sv[c][1] = 0.0; sv[c][2] = 0.0;
+		}
+	}
+	__syncthreads();
+	if (!active) return;
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+	for (int k = 0; k < UNROLL; ++k) {
+		a0 += m[k] * sv[k][0];
+		a1 += m[k] * sv[k][1];
+		a2 += m[k] * sv[k][2];
+	}
+	int c = UNROLL;
+	for (; c + UNROLL <= nc; c += UNROLL) {
+#pragma unroll
+		for (int k = 0; k < UNROLL; ++k) m[k] = __ldcs(M + (size_t)(c + k) * ld);
+#pragma unroll
+		for (int k = 0; k < UNROLL; ++k) {
+			a0 += m[k] * sv[c + k][0];
+			a1 += m[k] * sv[c + k][1];
+			a2 += m[k] * sv[c + k][2];
+		}
+	}
+	for (; c < nc; ++c) {
+		const double mm = __ldcs(M + (size_t)c * ld);
+		a0 += mm * sv[c][0];
+		a1 += mm * sv[c][1];
+		a2 += mm * sv[c][2];
+	}
+	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
 	red_add(vout + 3 * (size_t)go + 0, a0);
 	red_add(vout + 3 * (size_t)go + 1, a1);
 	red_add(vout + 3 * (size_t)go + 2, a2);
@@ -448,11 +522,18 @@ int direct_setup(admmb_ctx *ctx) {
 		S.grid = sms * (occ < 1 ? 1 : occ);
 		{
 			const char *e = getenv("ADMMB_SOLVE_MODE");
-			S.mode = 0;
-			if (e && e[0] >= '0' && e[0] <= '2') S.mode = e[0] - '0';
+			S.mode = 3;
+			if (e && e[0] >= '0' && e[0] <= '3') S.mode = e[0] - '0';
 			if (S.mode == 1 && occ < 1) S.mode = 0;
 			const char *u = getenv("ADMMB_SOLVE_UNROLL");
 			if (u) { const int v = atoi(u); if (v == 8 || v == 16 || v == 32) S.unroll = v; }
+			int occ_pf = 0;
+			if (S.unroll == 32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pf, k_solve_level_pf<32>, TILE_R, 0);
+			else if (S.unroll == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pf, k_solve_level_pf<16>, TILE_R, 0);
+			else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pf, k_solve_level_pf<8>, TILE_R, 0);
+			S.slots = sms * (occ_pf < 1 ? 1 : occ_pf);
+			const char *sp = getenv("ADMMB_SOLVE_SPLIT");
+			if (sp) { const int v = atoi(sp); S.split = (v == 1) ? 1 : (v == 2) ? 2 : (v == 4) ? 3 : 0; }
 		}
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
 	}
@@ -503,7 +584,16 @@ int direct_solve(admmb_ctx *ctx) {
 		const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
 		const SolveTile *tl = S.d_tiles.p + (ph < nl ? S.fwd_first[lv] : S.bwd_first[lv]);
 		if (cnt == 0) continue;
-		if (S.unroll == 32) k_solve_level<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
+		if (S.mode == 3) {
+			// column split: as long as twice the CTAs still fit the machine at once, halve the columns per CTA
+			int sl = 0;
+			if (S.split > 0) sl = S.split - 1;
+			else while (sl < 2 && (long)cnt * (2 << sl) <= (long)S.slots) ++sl;
+			const int g = cnt << sl;
+			if (S.unroll == 32) k_solve_level_pf<32><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
+			else if (S.unroll == 16) k_solve_level_pf<16><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
+			else k_solve_level_pf<8><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
+		} else if (S.unroll == 32) k_solve_level<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
 		else if (S.unroll == 16) k_solve_level<16><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
 		else k_solve_level<8><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
 		ctx->launches++;

@@ -347,7 +347,8 @@ public:
 		int admm_iters;
 		int device;      // (new) CUDA device of this system
 		int solver;      // (new) ADMMB_SOLVER_DIRECT / ADMMB_SOLVER_PCG
-		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT) {}
+		bool pin_host;   // (new) page-lock the storage of m_x / m_v so step() transfers it by direct DMA
+		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT), pin_host(true) {}
 	} settings;
 
 	double elapsed_s;
@@ -374,6 +375,17 @@ public:
 protected:
 	bool initialized;
 	admmb_ctx *ctx;
+	double *pinned[2] = { 0, 0 }; // storage of m_x / m_v currently page-locked (Settings::pin_host)
+	void pin_state() {
+		// Eigen may have reallocated m_x / m_v since the last step (resize): follow the storage
+		double *cur[2] = { m_x.data(), m_v.data() };
+		const long bytes[2] = { (long)(m_x.size() * sizeof(double)), (long)(m_v.size() * sizeof(double)) };
+		for (int k = 0; k < 2; ++k) {
+			if (!settings.pin_host || cur[k] == pinned[k]) continue;
+			if (pinned[k]) admmb_unregister_host_buffer(ctx, pinned[k]);
+			pinned[k] = (admmb_register_host_buffer(ctx, cur[k], bytes[k]) == 0) ? cur[k] : 0; // failure: staged path
+		}
+	}
 	struct BatchRef { int id; Force::B200Class cls; size_t first, count; };
 	std::vector<BatchRef> batches;
 	bool fail(const char *what) {
@@ -518,6 +530,7 @@ inline bool System::step() {
 		}
 		if (admmb_update_anchor_targets(ctx, batches[b].id, 0, (int)batches[b].count, pos.data(), act.data()) < 0) return fail("anchor targets");
 	}
+	pin_state();
 	if (admmb_step(ctx, settings.admm_iters, m_x.data(), m_v.data()) < 0) return fail("step");
 	// inactive control points follow the mesh (MovingAnchor::project writes point->pos, AnchorForce.cpp:82)
 	for (size_t b = 0; b < batches.size(); ++b) {
