@@ -624,6 +624,21 @@ extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
 	return ADMMB_OK;
 }
 
+extern "C" int admmb_download_x_f32(admmb_ctx *ctx, float *x3n) {
+	CHECK_READY(ctx);
+	if (!x3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "download_x_f32: null output");
+	const size_t n3 = 3 * (size_t)ctx->n;
+	float *d_tmp = reinterpret_cast<float *>(ctx->d_io.p);
+	int rc = launch_permute_out_f32(ctx, ctx->d_x.p, d_tmp);
+	if (rc) return rc;
+	const bool direct = is_registered(ctx, x3n, n3 * sizeof(float));
+	float *h_tmp = reinterpret_cast<float *>(ctx->h_pin);
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(direct ? x3n : h_tmp, d_tmp, n3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (!direct) staged_copy(x3n, h_tmp, n3 * sizeof(float));
+	return ADMMB_OK;
+}
+
 extern "C" int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout) {
 	CHECK_READY(ctx);
 	if (admm_iters < 0 || !x3n_inout || !v3n_inout) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step: bad arguments");

@@ -203,6 +203,7 @@ int launch_frame_end(admmb_ctx *ctx);
 int launch_rhs(admmb_ctx *ctx);
 int launch_permute_in(admmb_ctx *ctx, const double *d_src_user, double *d_dst_internal);
 int launch_permute_out(admmb_ctx *ctx, const double *d_src_internal, double *d_dst_user);
+int launch_permute_out_f32(admmb_ctx *ctx, const double *d_src_internal, float *d_dst_user);
 int pcg_setup(admmb_ctx *ctx);
 int pcg_solve(admmb_ctx *ctx);
 void pcg_destroy(admmb_ctx *ctx);

@@ -23,6 +23,22 @@ __global__ void __launch_bounds__(VEC_THREADS) k_permute_rows3(int n, const int 
 	else dst[t] = src[3 * (size_t)perm[i] + j];         // user -> internal
 }
 
+__global__ void __launch_bounds__(VEC_THREADS) k_permute_rows3_f32(int n, const int *__restrict__ perm, const double *__restrict__ src,
+                                                                   float *__restrict__ dst) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 3 * n) return;
+	const int i = t / 3, j = t - 3 * i;
+	dst[3 * (size_t)perm[i] + j] = __double2float_rn(src[t]); // internal -> user, (float) as the host cast rounds
+}
+
+int launch_permute_out_f32(admmb_ctx *ctx, const double *d_src_internal, float *d_dst_user) {
+	const int n = ctx->n;
+	k_permute_rows3_f32<<<(3 * n + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n, ctx->d_node_perm.p, d_src_internal, d_dst_user);
+	ctx->launches++;
+	ADMMB_CUDA(ctx, cudaGetLastError());
+	return ADMMB_OK;
+}
+
 int launch_permute_in(admmb_ctx *ctx, const double *d_src_user, double *d_dst_internal) {
 	const int n = ctx->n;
 	k_permute_rows3<<<(3 * n + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n, ctx->d_node_perm.p, d_src_user, d_dst_internal, 0);

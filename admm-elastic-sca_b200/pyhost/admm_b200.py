@@ -27,7 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
-    "admmb_register_host_buffer", "admmb_unregister_host_buffer",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
     L.admmb_add_collision.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_set_gravity.argtypes = [vp, C.c_int, _dp]
     L.admmb_register_host_buffer.argtypes = [vp, vp, C.c_long]
+    L.admmb_download_x_f32.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]
     L.admmb_unregister_host_buffer.argtypes = [vp, vp]
     L.admmb_add_explicit_subset.argtypes = [vp, C.c_int, _ip, _dp]
     L.admmb_add_wind.argtypes = [vp, C.c_int, _ip, _dp]
@@ -253,6 +254,12 @@ class System:
 
     def download(self):
         self._ck(self.L.admmb_download_xv(self.h, self.m_x.ctypes.data_as(C.c_void_p), self.m_v.ctypes.data_as(C.c_void_p)))
+
+    def positions_f32(self):
+        """Render hand-off: current device positions as float32 [n, 3] (SimContext::update's float sink)."""
+        out = np.empty(self.n3, dtype=np.float32)
+        self._ck(self.L.admmb_download_x_f32(self.h, out))
+        return out.reshape(-1, 3)
 
     def set_x(self, x):
         self.m_x[:] = _f64(x).reshape(-1)

@@ -224,3 +224,40 @@ def load_scene(path):
     sc["explicit"] = [res(e) for e in meta["explicit"]]
     sc["extra"] = {k[2:]: z[k] for k in z.files if k.startswith("x_") and k != "x_after_init"}
     return sc
+
+
+# ---- trajectory hand-off: TetGen .node / .ele as the reference writes them -------------------------------------
+def save_tetmesh(filename, x, tets=None):
+    """TetMesh::save (M/src/TetMesh.cpp:306-352): `<filename>.node` (and `<filename>.ele` when tets are given) in
+    TetGen format.  Coordinates go through float and are printed at the default stream precision, as trimesh's
+    Vec::str does (Vec.h:229-237) -- i.e. '%g'."""
+    xf = np.asarray(x, dtype=np.float32).reshape(-1, 3)
+    with open(filename + ".node", "w") as f:
+        f.write(f"{xf.shape[0]} 3 0 0\n")
+        for i, p in enumerate(xf):
+            f.write("\t%d %g %g %g\n" % (i, p[0], p[1], p[2]))
+        f.write("# Generated by mclscene (www.mattoverby.net)")
+    if tets is not None:
+        t = np.asarray(tets, dtype=np.int64).reshape(-1, 4)
+        with open(filename + ".ele", "w") as f:
+            f.write(f"{t.shape[0]} 4 0\n")
+            for i, e in enumerate(t):
+                f.write("\t%d %d %d %d %d\n" % (i, e[0], e[1], e[2], e[3]))
+            f.write("# Generated by mclscene (www.mattoverby.net)")
+
+
+def load_tetmesh(filename):
+    """Reads `<filename>.node` (and `.ele` if present) back: (x float32 [n, 3], tets int32 [T, 4] or None)."""
+    import os
+
+    def rows(path):
+        with open(path) as f:
+            return [ln.split() for ln in f if ln.strip() and not ln.lstrip().startswith("#")]
+    r = rows(filename + ".node")
+    n = int(r[0][0])
+    x = np.array([[float(v) for v in q[1:4]] for q in r[1:1 + n]], dtype=np.float32)
+    tets = None
+    if os.path.exists(filename + ".ele"):
+        r = rows(filename + ".ele")
+        tets = np.array([[int(v) for v in q[1:5]] for q in r[1:1 + int(r[0][0])]], dtype=np.int32)
+    return x, tets

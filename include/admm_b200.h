@@ -138,6 +138,10 @@ int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames);
 int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n);   /* either may be NULL */
 int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n);             /* either may be NULL */
 
+/* Render hand-off (SimContext::update, src/SimContext.cpp:176-195: m_x -> float `trimesh::point`s): current positions
+ * rounded to float on the device, user node order; half the bytes of admmb_download_xv(x, NULL) and no v. */
+int admmb_download_x_f32(admmb_ctx *ctx, float *x3n);
+
 /* Optional: page-lock a caller-owned host buffer (e.g. the storage of System::m_x / m_v) so that admmb_step /
  * admmb_upload_xv / admmb_download_xv transfer it directly instead of staging it through the context's own pinned
  * area.  The buffer must stay allocated until it is unregistered (admmb_destroy unregisters what is left).  Buffers
