@@ -287,8 +287,12 @@ static int upload_batch(admmb_ctx *ctx, Batch &b) {
 static int setup_solver(admmb_ctx *ctx) {
 	auto t0 = std::chrono::steady_clock::now();
 	assemble_system(ctx);
+	auto t1 = std::chrono::steady_clock::now();
 	int rc = (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_setup(ctx) : direct_setup(ctx);
 	ctx->factor_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (getenv("ADMMB_FACTOR_VERBOSE"))
+		fprintf(stderr, "[setup] assemble A_n %.3f s, solver setup %.3f s\n", std::chrono::duration<double>(t1 - t0).count(),
+		        ctx->factor_seconds - std::chrono::duration<double>(t1 - t0).count());
 	return rc;
 }
 

@@ -211,6 +211,9 @@ void pcg_destroy(admmb_ctx *ctx);
 int dist_allgather_nodes(admmb_ctx *ctx, double *vec);            // in place: every rank contributes its owned rows
 int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count);
 void dist_destroy(admmb_ctx *ctx);
+// front_gpu.cu
+struct FrontBackend;
+FrontBackend *make_device_front_backend(admmb_ctx *ctx);
 // direct_solve.cu
 void direct_set_blocks(admmb_ctx *ctx, const std::vector<int> &block_end);
 void direct_fill_info(const admmb_ctx *ctx, admmb_info *out);

@@ -7,6 +7,9 @@
 #include "direct_factor.h"
 
 #include <omp.h>
+#include <memory>
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <chrono>
@@ -185,7 +188,7 @@ void panel_times_inverse(int r, int w, const double *L21, long ldl, const double
 } // namespace
 
 int supernodal_factorize(int n, const int *Ap, const int *Ai, const double *Ax, const std::vector<int> &block_end,
-                         SupernodalFactor &F, std::string &err) {
+                         SupernodalFactor &F, std::string &err, FrontBackend *backend) {
 	auto t0 = std::chrono::steady_clock::now();
 	const int nb = (int)block_end.size();
 	F = SupernodalFactor();
@@ -244,19 +247,31 @@ int supernodal_factorize(int n, const int *Ap, const int *Ai, const double *Ax, 
 	auto t1 = std::chrono::steady_clock::now();
 	std::vector<std::vector<int> > by_level(F.nlevels);
 	for (int J = 0; J < nb; ++J) by_level[F.level[J]].push_back(J);
-	std::vector<std::vector<double> > update(nb); // Schur complements waiting for their parent (|R| x |R|, lower)
+	std::vector<std::unique_ptr<double[]> > update(nb); // Schur complements waiting for their parent (|R| x |R|, lower; not zero-filled)
 	const int nthreads = omp_get_max_threads();
 	std::vector<std::vector<int> > relpos_t(nthreads, std::vector<int>(n, -1));
 	bool failed = false;
 	int fail_col = -1;
 
+	const bool verbose = getenv("ADMMB_FACTOR_VERBOSE") != nullptr;
+	double t_phase[4] = { 0, 0, 0, 0 }; // assemble + extend-add, partial Cholesky, inverse, panel x inverse (serial levels only)
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
 	auto process = [&](int J, bool par, std::vector<int> &relpos) {
+		auto p0 = now();
 		const int c0 = F.start[J], w = F.start[J + 1] - c0;
 		const int *R = F.rows.data() + F.rptr[J];
 		const int r = F.rptr[J + 1] - F.rptr[J];
 		const int m = w + r;
-		std::vector<double> Fr((size_t)m * m, 0.0);
 		const long ld = m;
+		// the front: on the host heap, or -- for the large fronts that go to the device backend -- in its page-locked buffer
+		const bool dev = backend && par && m >= backend->min_front();
+		std::unique_ptr<double[]> Fr_heap;
+		double *Fr = dev ? backend->front_buffer((size_t)m * m) : nullptr;
+		const bool on_dev = Fr != nullptr;
+		if (!on_dev) { Fr_heap.reset(new double[(size_t)m * m]); Fr = Fr_heap.get(); } // zeroed below, in parallel for large fronts
+#pragma omp parallel for schedule(static) if (par && m > 512)
+		for (int c = 0; c < m; ++c) std::memset(Fr + (size_t)c * m, 0, sizeof(double) * (size_t)m);
 		for (int c = 0; c < w; ++c) relpos[c0 + c] = c;
 		for (int k = 0; k < r; ++k) relpos[R[k]] = w + k;
 		// assemble the original entries of the supernode's columns (lower part)
@@ -267,52 +282,100 @@ int supernodal_factorize(int n, const int *Ap, const int *Ai, const double *Ax, 
 				if (i >= j) Fr[relpos[i] + (long)c * ld] += Ax[p];
 			}
 		}
-		// extend-add the children's Schur complements
+		// extend-add the children's Schur complements (distinct destination columns: parallel over the child's columns)
 		for (int K : children[J]) {
 			const int *RK = F.rows.data() + F.rptr[K];
 			const int rk = F.rptr[K + 1] - F.rptr[K];
-			const std::vector<double> &U = update[K];
+			const double *U = update[K].get();
 			std::vector<int> loc(rk);
 			for (int a = 0; a < rk; ++a) loc[a] = relpos[RK[a]];
+#pragma omp parallel for schedule(dynamic, 16) if (par && rk > 256)
 			for (int b = 0; b < rk; ++b) {
-				double *dst = Fr.data() + (long)loc[b] * ld;
-				const double *src = U.data() + (size_t)b * rk;
+				double *dst = Fr + (long)loc[b] * ld;
+				const double *src = U + (size_t)b * rk;
 				for (int a = b; a < rk; ++a) dst[loc[a]] += src[a];
 			}
-			std::vector<double>().swap(update[K]);
+			update[K].reset();
 		}
-		if (!partial_chol(m, w, Fr.data(), ld, par)) {
+		auto p1 = now();
+		double *T = F.T.data() + F.toff[J];
+		const bool want_U = r > 0 && F.parent[J] >= 0;
+		if (on_dev) {
+			if (want_U) update[J].reset(new double[(size_t)r * r]);
+			const int rc = backend->factor_front(m, w, Fr, T, want_U ? update[J].get() : nullptr);
+			if (rc == 0) {
+				F.device_fronts++;
+				t_phase[0] += secs(p0, p1); t_phase[1] += secs(p1, now());
+				return;
+			}
+			if (rc > 0) {
+#pragma omp critical
+				{ failed = true; fail_col = c0; }
+				return;
+			}
+			// backend failure: the assembled front is intact, continue on the host
+		}
+		if (!partial_chol(m, w, Fr, ld, par)) {
 #pragma omp critical
 			{ failed = true; fail_col = c0; }
 			return;
 		}
-		double *T = F.T.data() + F.toff[J];
-		tri_inverse(w, Fr.data(), ld, T, ld, par);
-		panel_times_inverse(r, w, Fr.data() + w, ld, T, ld, T + w, ld, par);
+		auto p2 = now();
+		tri_inverse(w, Fr, ld, T, ld, par);
+		auto p3 = now();
+		panel_times_inverse(r, w, Fr + w, ld, T, ld, T + w, ld, par);
+		if (par) { t_phase[0] += secs(p0, p1); t_phase[1] += secs(p1, p2); t_phase[2] += secs(p2, p3); t_phase[3] += secs(p3, now()); }
 		// note: panel_times_inverse leaves +L21*X in G (it negates the -product gemm_sub produced)
-		if (r > 0 && F.parent[J] >= 0) {
-			std::vector<double> &U = update[J];
-			U.resize((size_t)r * r);
+		if (want_U) {
+			update[J].reset(new double[(size_t)r * r]);
+			double *U = update[J].get();
+#pragma omp parallel for schedule(static) if (par && r > 512)
 			for (int b = 0; b < r; ++b)
-				std::memcpy(U.data() + (size_t)b * r + b, Fr.data() + (w + b) + (long)(w + b) * ld, sizeof(double) * (r - b));
+				std::memcpy(U + (size_t)b * r + b, Fr + (w + b) + (long)(w + b) * ld, sizeof(double) * (r - b));
 		}
 	};
 
+	if (backend) {
+		size_t mf = 0, mp = 0;
+		for (int J = 0; J < nb; ++J) {
+			const size_t w = F.start[J + 1] - F.start[J], m = w + (F.rptr[J + 1] - F.rptr[J]);
+			if ((int)m >= backend->min_front()) { mf = std::max(mf, m * m); mp = std::max(mp, m * w); }
+		}
+		if (mf) backend->reserve(mf, mp);
+	}
 	for (int lv = 0; lv < F.nlevels && !failed; ++lv) {
 		const std::vector<int> &L = by_level[lv];
-		if ((int)L.size() >= 2 * nthreads) {
+		auto tl0 = now();
+		// large fronts one at a time (parallel inside the front, or on the device); the rest of the level tree-parallel
+		std::vector<int> big, small;
+		for (int J : L) {
+			const int m = (F.start[J + 1] - F.start[J]) + (F.rptr[J + 1] - F.rptr[J]);
+			((backend && m >= backend->min_front()) ? big : small).push_back(J);
+		}
+		for (int J : big) {
+			if (failed) break;
+			process(J, true, relpos_t[0]);
+		}
+		if ((int)small.size() >= 2 * nthreads) {
 #pragma omp parallel for schedule(dynamic, 1)
-			for (long t = 0; t < (long)L.size(); ++t) {
+			for (long t = 0; t < (long)small.size(); ++t) {
 				if (failed) continue;
-				process(L[t], false, relpos_t[omp_get_thread_num()]);
+				process(small[t], false, relpos_t[omp_get_thread_num()]);
 			}
 		} else {
-			for (int J : L) {
+			for (int J : small) {
 				if (failed) break;
 				process(J, true, relpos_t[0]);
 			}
 		}
+		if (verbose) {
+			long wmax = 0, mmax = 0;
+			for (int J : L) { wmax = std::max<long>(wmax, F.start[J + 1] - F.start[J]); mmax = std::max<long>(mmax, F.start[J + 1] - F.start[J] + F.rptr[J + 1] - F.rptr[J]); }
+			fprintf(stderr, "[factor] level %2d: %6zu supernodes (max width %ld, max front %ld), %zu large + %zu %s: %.3f s\n", lv, L.size(), wmax, mmax,
+			        big.size(), small.size(), (int)small.size() >= 2 * nthreads ? "tree-parallel " : "front-parallel", secs(tl0, now()));
+		}
 	}
+	if (verbose) fprintf(stderr, "[factor] one-at-a-time fronts: assemble %.3f  cholesky (or whole device front) %.3f  inverse %.3f  panel*inverse %.3f s; %d fronts on the device\n", t_phase[0], t_phase[1], t_phase[2], t_phase[3], F.device_fronts);
 	F.seconds_numeric = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
 	if (failed) {
 		char buf[160];

@@ -35,7 +35,7 @@ class Info(C.Structure):
     _fields_ = [("n_nodes", C.c_int), ("n_batches", C.c_int), ("solver", C.c_int), ("n_rows", C.c_long),
                 ("nnz_A", C.c_long), ("nnz_L", C.c_long), ("n_supernodes", C.c_int), ("n_levels", C.c_int),
                 ("factor_bytes", C.c_long), ("factor_seconds", C.c_double), ("cg_iters_total", C.c_long),
-                ("launches_total", C.c_long), ("elapsed_s", C.c_double)]
+                ("launches_total", C.c_long), ("elapsed_s", C.c_double), ("device_fronts", C.c_int)]
 
 
 _lib = None

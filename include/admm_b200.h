@@ -183,6 +183,7 @@ typedef struct admmb_info {
 	long cg_iters_total;    /* PCG iterations since finalize */
 	long launches_total;    /* kernel launches issued by this context since finalize */
 	double elapsed_s;       /* System::elapsed_s */
+	int device_fronts;      /* fronts of the last factorisation whose dense work ran on the device (0 = all on the host) */
 } admmb_info;
 int admmb_get_info(admmb_ctx *ctx, admmb_info *out);
 
