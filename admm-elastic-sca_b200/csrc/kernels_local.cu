@@ -21,11 +21,14 @@ namespace admmb {
 #ifndef LOCAL_THREADS
 #define LOCAL_THREADS 128
 #endif
+// Hyperelastic kernel shape, measured on the 1 M-tet cube (steady state, ms per launch): 256 x 3 blocks (80 registers,
+// 24 warps / SM) 0.920; 320 x 2 (96 registers, 20 warps) 0.898; 256 x 2 (128 registers) 0.919; 288 x 2 0.979;
+// 192 x 3 0.977; 256 x 4 (64 registers) 1.047; 128 x 6 1.007.  Fewer spills beat more warps up to 96 registers.
 #ifndef HYPER_THREADS
-#define HYPER_THREADS 256
+#define HYPER_THREADS 320
 #endif
 #ifndef HYPER_MIN_BLOCKS
-#define HYPER_MIN_BLOCKS 3
+#define HYPER_MIN_BLOCKS 2
 #endif
 
 template <int KIND, int MH>
