@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <numeric>
+#include <omp.h>
 
 #include "common.h"
 
@@ -218,6 +219,11 @@ extern "C" int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *i
 extern "C" int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3) {
 	if (!ctx) return ADMMB_E_ARG;
 	return add_explicit(ctx, 2, ntris, tris3, 3, dir3, "wind");
+}
+
+extern "C" int admmb_set_host_threads(int n) {
+	omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+	return ADMMB_OK;
 }
 
 extern "C" int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters) {

@@ -181,10 +181,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    if world > 1 and "OMP_NUM_THREADS" not in os.environ:
-        # every rank factors its own scene on the host: share the cores instead of oversubscribing them
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import admm_b200
+    if world > 1:
+        # every rank factors its own scene on the host: share the cores instead of oversubscribing them (torchrun
+        # exports OMP_NUM_THREADS=1, which would leave all but one core per rank idle during setup)
+        admm_b200.lib().admmb_set_host_threads(max(1, (os.cpu_count() or 1) // world))
     sc = make_scene(args.cube)
     ntets = sc["batches"][0]["idx"].shape[0]
     nverts = sc["x"].shape[0]

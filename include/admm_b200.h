@@ -98,6 +98,10 @@ int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3);
 int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *idx, const double *dir3);
 int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3);
 
+/* Host threads (OpenMP) used by the setup path of every context in this process (ordering, factorisation, tile
+ * packing); n <= 0 restores the OpenMP default.  Several ranks on one node should share the cores: cores / ranks each. */
+int admmb_set_host_threads(int n);
+
 /* Solver choice and tolerances; call before admmb_finalize.  tol and max_cg_iters apply to PCG only. */
 int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters);
 
