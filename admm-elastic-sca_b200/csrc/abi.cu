@@ -713,7 +713,7 @@ extern "C" int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n) {
 	return ADMMB_OK;
 }
 
-extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
+extern "C" int admmb_step_resident_async(admmb_ctx *ctx, int admm_iters, int frames) {
 	CHECK_READY(ctx);
 	if (admm_iters < 0 || frames < 1) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step_resident: bad arguments");
 	const bool timed = ctx->timing.on;
@@ -727,14 +727,27 @@ extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
 		if ((rc = run_iterations(ctx, admm_iters))) return rc;
 		if ((rc = launch_frame_end(ctx))) return rc;
 		ctx->elapsed_s += ctx->dt;
-		if (timed) { e1 = next_event(ctx); if ((rc = collect_timing(ctx, admm_iters, e0, e1))) return rc; }
+		if (timed) { e1 = next_event(ctx); if ((rc = collect_timing(ctx, admm_iters, e0, e1))) return rc; } // (phase timing synchronises)
 	}
 	ADMMB_CUDA(ctx, cudaEventRecord(ctx->ev_region[1], ctx->stream));
-	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	float ms = 0.f;
-	ADMMB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_region[0], ctx->ev_region[1]));
-	ctx->last_region_ms = ms;
 	return ADMMB_OK;
+}
+
+extern "C" int admmb_sync(admmb_ctx *ctx) {
+	CHECK_READY(ctx);
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->ev_region[0]) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, ctx->ev_region[0], ctx->ev_region[1]) == cudaSuccess) ctx->last_region_ms = ms;
+		else cudaGetLastError();
+	}
+	return ADMMB_OK;
+}
+
+extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {
+	int rc = admmb_step_resident_async(ctx, admm_iters, frames);
+	if (rc) return rc;
+	return admmb_sync(ctx);
 }
 
 extern "C" int admmb_last_region_ms(admmb_ctx *ctx, double *ms) {

@@ -27,7 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
-    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync",
 ]
 
 
@@ -76,6 +76,8 @@ def lib():
     L.admmb_debug_local_step.argtypes = [vp, _dp]
     L.admmb_debug_global_step.argtypes = [vp, _dp]
     L.admmb_step_resident.argtypes = [vp, C.c_int, C.c_int]
+    L.admmb_step_resident_async.argtypes = [vp, C.c_int, C.c_int]
+    L.admmb_sync.argtypes = [vp]
     L.admmb_upload_xv.argtypes = [vp, vp, vp]
     L.admmb_download_xv.argtypes = [vp, vp, vp]
     L.admmb_update_anchor_targets.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -249,6 +251,13 @@ class System:
 
     def step_resident(self, frames=1, iters=None):
         self._ck(self.L.admmb_step_resident(self.h, int(self.admm_iters if iters is None else iters), int(frames)))
+
+    def step_resident_async(self, frames=1, iters=None):
+        """Enqueue only (scene ensembles: several Systems in flight on one GPU); pair with sync()."""
+        self._ck(self.L.admmb_step_resident_async(self.h, int(self.admm_iters if iters is None else iters), int(frames)))
+
+    def sync(self):
+        self._ck(self.L.admmb_sync(self.h))
 
     def upload(self):
         self._ck(self.L.admmb_upload_xv(self.h, self.m_x.ctypes.data_as(C.c_void_p), self.m_v.ctypes.data_as(C.c_void_p)))

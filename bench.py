@@ -149,6 +149,84 @@ def cpu_baseline_leg(N):
                       f"scaled x{ntets}/{FULL_TETS}; initialize() {t_init:.1f} s excluded"}
 
 
+def run_ensemble(args, rank, world, local_rank, torch, dist, admm_b200):
+    """Scene ensemble: independent scenes, one context (and stream, and CUDA graph) each, round-robin over the ranks, no
+    data-path collective.  All scenes of a rank are enqueued before any is waited for, so they overlap on the GPU."""
+    import ensemble
+    import scenes
+    mine = ensemble.scene_shard(args.ensemble, rank, world)
+    sims = []
+    t0 = time.perf_counter()
+    for sidx in mine:
+        # per-copy seed: every scene starts from its own perturbed stretch (SURVEY 8d: "per-copy seed")
+        sc = scenes.cube_scene(args.ens_cube, kind=scenes.TET_NH, mu=1e5, lam=1e5, maxit=5, mass=1000.0, dt=0.04, iters=ADMM_ITERS,
+                               stretch=1.3, seed=1000 + sidx)
+        sim = admm_b200.System(sc, device=local_rank)
+        sim.set_x(sc["x_after_init"])
+        sim.upload()
+        sims.append(sim)
+    t_setup = time.perf_counter() - t0
+    ntets = sims[0].scene["batches"][0]["idx"].shape[0] if sims else 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(frames):
+        for s in sims:
+            s.step_resident_async(frames=frames)
+        for s in sims:
+            s.sync()
+
+    run(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = sum(s.info()["launches_total"] for s in sims)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()                       # idle stream: completes at once -> a device timestamp of "now"
+    run(args.steps)                    # the timed region: K frames of every scene of this rank
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_region = ev0.elapsed_time(ev1)
+    l1 = sum(s.info()["launches_total"] for s in sims)
+    clocks = sampler.stop()
+    barrier()
+    # end to end: every scene through admmb_step with host buffers, one after the other (the call is synchronous)
+    for s in sims:
+        s.download()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for s in sims:
+            s.step()
+    torch.cuda.synchronize()
+    sec_e2e = time.perf_counter() - t0
+    barrier()
+    ms_max, frames_total = ensemble.reduce_job(ms_region, args.steps * len(sims))
+    ms_e2e_max, _ = ensemble.reduce_job(sec_e2e * 1e3, args.steps * len(sims))
+    if rank == 0:
+        nverts = sims[0].n3 // 3
+        line = {
+            "metric": "ensemble_scene_frames_per_s", "value": frames_total / (ms_max * 1e-3), "unit": "scene-frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.ensemble} independent scenes: cube N={args.ens_cube} ({ntets} tets, {nverts} nodes) NeoHookean mu=lambda=1e5 "
+                                   f"max_iterations=5, {ADMM_ITERS} ADMM iterations per frame, per-copy seed",
+                       "parallelism": f"scenes round-robin over {world} rank(s), {len(sims)} scenes in flight per GPU on their own streams, no collective",
+                       "l2": "64 scenes x (factor + force arrays) exceed the L2 together; scenes interleave, no flush"},
+            "admm_iterations_per_s": frames_total * ADMM_ITERS / (ms_max * 1e-3),
+            "e2e": {"value": frames_total / (ms_e2e_max * 1e-3), "unit": "scene-frames/s", "h2d_bytes_per_step": len(sims) * 2 * 3 * nverts * 8,
+                    "d2h_bytes_per_step": len(sims) * 2 * 3 * nverts * 8, "note": "scenes stepped one after the other through the synchronous admmb_step"},
+            "gpu_launches": int(l1 - l0), "clocks": clocks, "setup": {"seconds": t_setup, "scenes_on_rank0": len(sims)},
+        }
+        print(json.dumps(line))
+    for s in sims:
+        s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +237,10 @@ def main():
     ap.add_argument("--ref-cube", type=int, default=30, help="cube resolution of the reference arm's bounded sample")
     ap.add_argument("--cpu-cube", type=int, default=20, help="cube resolution of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ensemble", type=int, default=0,
+                    help="scene-ensemble mode (BASELINE configs[4] '64-scene ensemble'): this many independent scenes (cube --ens-cube) dealt "
+                         "round-robin to the ranks, all scenes of a rank in flight at once on their own streams; prints scene-frames/s")
+    ap.add_argument("--ens-cube", type=int, default=20, help="cube resolution of the ensemble scenes (N=20: 48,000 tets)")
     ap.add_argument("--solver", default="direct", choices=["direct", "pcg"])
     ap.add_argument("--partition", action="store_true",
                     help="N > 1: ONE mesh partitioned over the ranks (PCG rows + local step, NCCL all-gather / all-reduce) instead of "
@@ -186,6 +268,9 @@ def main():
         # every rank factors its own scene on the host: share the cores instead of oversubscribing them (torchrun
         # exports OMP_NUM_THREADS=1, which would leave all but one core per rank idle during setup)
         admm_b200.lib().admmb_set_host_threads(max(1, (os.cpu_count() or 1) // world))
+    if args.ensemble > 0:
+        run_ensemble(args, rank, world, local_rank, torch, dist, admm_b200)
+        return
     sc = make_scene(args.cube)
     ntets = sc["batches"][0]["idx"].shape[0]
     nverts = sc["x"].shape[0]

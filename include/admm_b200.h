@@ -139,6 +139,11 @@ int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n);
 
 /* Same step with x and v kept resident on the device (no host copies); frames >= 1 consecutive steps. */
 int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames);
+/* The same without the final synchronisation: the frames are only enqueued on the context's stream, so one host thread
+ * can keep several contexts (scene ensembles: one context per scene) running concurrently on one GPU.  admmb_sync
+ * waits for the context's stream and fills admmb_last_region_ms. */
+int admmb_step_resident_async(admmb_ctx *ctx, int admm_iters, int frames);
+int admmb_sync(admmb_ctx *ctx);
 int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n);   /* either may be NULL */
 int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n);             /* either may be NULL */
 
