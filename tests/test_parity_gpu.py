@@ -49,16 +49,16 @@ def _worst(a, g):
 
 
 # ---- teacher-forced: one iteration at a time from the reference's inputs -----------------------------------
-@pytest.mark.parametrize("name", list(SCEN))
-def test_iteration_teacher_forced(name):
-    gold, scenario = _load(name)
+def _replay(gold, scenario, u0=None, prox0=None):
+    """Replays every ADMM iteration of `gold` (reference dumps) on the device from the reference's own inputs.
+    Returns (vectors bit-exact, vectors compared, worst rel-L2 of the local step, worst rel-L2 of x after the solve)."""
     ad = DevAdapter(scenario["scene"], solver=SOLVERS["direct"])
     sim = ad.sim
     F, K = gold["x_it"].shape[:2]
     R = gold["z_it"].shape[2]
-    has_prox = "prox_it" in gold.files and gold["prox_it"].size > 0
-    u_prev = np.zeros(R)
-    prox_prev = np.ones(gold["prox_it"].shape[2:]) if has_prox else None
+    has_prox = "prox_it" in gold and gold["prox_it"].size > 0
+    u_prev = np.zeros(R) if u0 is None else u0
+    prox_prev = (np.ones(gold["prox_it"].shape[2:]) if prox0 is None else prox0) if has_prox else None
     ev = scenario.get("events")
     n_exact = n_total = 0
     worst_local = worst_x = 0.0
@@ -90,6 +90,14 @@ def test_iteration_teacher_forced(name):
             if has_prox:
                 prox_prev = gold["prox_it"][f, k]
     ad.close()
+    return n_exact, n_total, worst_local, worst_x
+
+
+@pytest.mark.parametrize("name", list(SCEN))
+def test_iteration_teacher_forced(name):
+    gold, scenario = _load(name)
+    gold = {k: gold[k] for k in gold.files}
+    n_exact, n_total, worst_local, worst_x = _replay(gold, scenario)
     print(f"{name}: local step bit-exact in {n_exact}/{n_total} vectors, worst rel-L2 {worst_local:.2e}; "
           f"global step worst rel-L2 of x {worst_x:.2e}")
     assert worst_local <= TOL_ITER
@@ -104,6 +112,51 @@ def test_iteration_teacher_forced(name):
         pass
     else:
         assert n_exact == n_total, f"{name}: {n_total - n_exact} of {n_total} local-step vectors differ in the last bits"
+
+
+@pytest.mark.parametrize("N,kind,label,frames", [(16, scenes.TET_NH, "nh", 4), (12, scenes.TET_STVK, "stvk", 3), (14, scenes.TET_ARAP, "arap", 2)])
+def test_live_teacher_forced_midsize(N, kind, label, frames):
+    """The same replay against the UNMODIFIED reference run here and now on a mesh ~100x the size of the committed
+    goldens (24 576 NeoHookean tets: several waves of the local kernel, a 9-level elimination tree): the dumps are too
+    large to commit, oracle/_ref travels with the snapshot instead."""
+    if not have_ref():
+        pytest.skip("oracle/_ref/libadmm_ref.so not present on this box")
+    scenario = dict(scene=scenes.cube_scene(N, kind=kind, seed=5), frames=frames)
+    ra = RefAdapter(scenario["scene"])
+    gold = run_scenario(ra, scenario, dump=True)
+    ra.close()
+    n_exact, n_total, worst_local, worst_x = _replay(gold, scenario)
+    ntets = scenario["scene"]["batches"][0]["idx"].shape[0]
+    print(f"live teacher-forced {label} N={N} ({ntets} tets, {frames} frames): local step bit-exact in {n_exact}/{n_total} vectors, "
+          f"global step worst rel-L2 {worst_x:.1e}")
+    assert n_exact == n_total
+    assert worst_x <= TOL_ITER
+
+
+def test_live_teacher_forced_steady_state():
+    """The benchmark regime: after 20 frames the reference's line search runs to its maxfev = 20 cap in (almost) every
+    tet.  The reference is stepped 20 frames here, then frames 21 and 22 are replayed on the device
+    from its dumps -- 48 000 NeoHookean tets, every vector bit for bit."""
+    if not have_ref():
+        pytest.skip("oracle/_ref/libadmm_ref.so not present on this box")
+    sc = scenes.cube_scene(20, kind=scenes.TET_NH, seed=None)
+    ra = RefAdapter(sc)
+    ra.set_x(sc["x_after_init"])
+    for _ in range(19):
+        ra.step()
+    _, _, ui, _, _ = ra.step_dump()                      # frame 20: its last u and optimiser state start the replay
+    u0, prox0 = ui[-1].copy(), ra.last_prox_it[-1].copy()
+    out = dict(x_it=[], z_it=[], u_it=[], x=[], prox_it=[])
+    for _ in range(2):
+        xi, zi, ui, x, _ = ra.step_dump()
+        out["x_it"].append(xi); out["z_it"].append(zi); out["u_it"].append(ui); out["x"].append(x); out["prox_it"].append(ra.last_prox_it)
+    ra.close()
+    gold = {k: np.array(v) for k, v in out.items()}
+    n_exact, n_total, worst_local, worst_x = _replay(gold, dict(scene=sc, frames=2), u0=u0, prox0=prox0)
+    print(f"live teacher-forced steady state (48000 tets, frames 21-22): local step bit-exact in {n_exact}/{n_total} vectors, "
+          f"global step worst rel-L2 {worst_x:.1e}")
+    assert n_exact == n_total
+    assert worst_x <= TOL_ITER
 
 
 # ---- free-running --------------------------------------------------------------------------------------------
