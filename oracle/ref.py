@@ -57,6 +57,7 @@ def lib():
                   "ref_get_force_weights"):
             getattr(L, f).argtypes = [C.c_void_p, _dp]
         L.ref_get_prox_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_set_prox_state.argtypes = [C.c_void_p, _dp]
         L.ref_get_prox_iters.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_step.argtypes = [C.c_void_p]
         L.ref_step_dump.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_void_p]
@@ -177,6 +178,12 @@ class RefSystem:
         if n:
             self.L.ref_get_prox_state(self.h, out.ctypes.data_as(C.c_void_p))
         return out
+
+    def set_prox_state(self, st):
+        self.L.ref_set_prox_state(self.h, _f64(st).reshape(-1))
+
+    def set_u(self, u):
+        self.L.ref_set_u(self.h, _f64(u).reshape(-1))
 
     def prox_iters(self):
         n = self.L.ref_get_prox_iters(self.h, None)

@@ -349,6 +349,18 @@ int ref_get_prox_state(void *h, double *out4) {
 	}
 	return c;
 }
+// Setter for the same state (teacher-forced replays that start in the middle of a run).
+int ref_set_prox_state(void *h, const double *in4) {
+	Shim *s = (Shim *)h; int c = 0;
+	for (size_t i = 0; i < s->sys.forces.size(); ++i) {
+		HyperElasticTet *t = dynamic_cast<HyperElasticTet *>(s->sys.forces[i].get());
+		if (!t) continue;
+		for (int j = 0; j < 3; ++j) t->last_prox_result[j] = in4[4 * c + j];
+		t->solver->settings_.init_hess = in4[4 * c + 3];
+		++c;
+	}
+	return c;
+}
 // L-BFGS outer-iteration counts of the last project() per hyperelastic tet
 int ref_get_prox_iters(void *h, int *out) {
 	Shim *s = (Shim *)h; int c = 0;
