@@ -34,8 +34,8 @@ METRIC = "admm_iterations_per_s_cube_1M_tets"
 UNIT = "ADMM iterations/s"
 ADMM_ITERS = 10
 FULL_TETS = 998250  # N = 55
-EXEC_FP64_FLOPS_PER_TET_ITER = 9288      # profiles/r1d_local.txt (steady state): (1157.8 + 1295.3 + 2 x 1444.6) flops/clk x 1.7356 Mclk / 998250 tets
-SOLVE_DRAM_BYTES_NCU = 1.7191e9          # profiles/r1d_solve.txt: dram bytes read+written by the 26 launches of one solve (cube N=55)
+EXEC_FP64_FLOPS_PER_TET_ITER = 9301      # profiles/r1e_local.txt (steady state): (1184.0 + 1325.7 + 2 x 1477.5) flops/clk x 1.6991 Mclk / 998250 tets
+SOLVE_DRAM_BYTES_NCU = 1.7221e9          # profiles/r1e_solve.txt: dram bytes read+written by the 26 launches of one solve (cube N=55)
 
 
 def peaks():
@@ -354,14 +354,14 @@ def main():
                 "frac": solve_gbs / hbm_peak, "traffic": SOLVE_DRAM_BYTES_NCU if args.cube == 55 else None, "peak_source": peak_src,
                 "share_of_step": solve_ms / (local_ms + rhs_ms + solve_ms),
                 "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; "
-                        f"{info0['n_levels']} levels; traffic = dram bytes of these launches summed, ncu profiles/r1d_solve.txt (cube N=55 only)"}
+                        f"{info0['n_levels']} levels; traffic = dram bytes of these launches summed, ncu profiles/r1e_solve.txt (cube N=55 only)"}
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
         fp64_peak = 148 * 64 * 2 * sm_clock / 1e12   # 64 DFMA lanes per SM per clock (ncu: sm__sass_thread_inst_executed_op_dfma peak)
         local_tflops = EXEC_FP64_FLOPS_PER_TET_ITER * ntets / (local_ms * 1e-3) / 1e12 if local_ms > 0 else 0.0
         roof_local = {"bound": "fp64", "kernel": "k_local_tets_hyper<NHModel,5>", "achieved": local_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                       "frac": local_tflops / fp64_peak, "share_of_step": local_ms / (local_ms + rhs_ms + solve_ms),
-                      "fp64_pipe_active_pct_ncu": 57.0, "algorithmic_GBps": local_gbs,
-                      "note": "executed FP64 flops per tet-iteration in steady state (DADD + DMUL + 2 DFMA, ncu profiles/r1d_local.txt: "
+                      "fp64_pipe_active_pct_ncu": 57.9, "algorithmic_GBps": local_gbs,
+                      "note": "executed FP64 flops per tet-iteration in steady state (DADD + DMUL + 2 DFMA, ncu profiles/r1e_local.txt: "
                               f"{EXEC_FP64_FLOPS_PER_TET_ITER}); peak = 148 SMs x 64 DFMA/clk x 2 at the sampled SM clock; the kernel is compiled "
                               "with -fmad=false to stay bit-exact with the reference, so no multiply-add is fused"}
         line = {
