@@ -46,12 +46,15 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The sampler is started
+    before the warm-up (nvidia-smi needs a few hundred ms to come up -- longer than a short timed region) and every row
+    carries nvidia-smi's own timestamp, so only the rows that fall inside [begin(), end()] are used."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -59,6 +62,9 @@ class ClockSampler:
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + 5.0          # nvidia-smi takes a few hundred ms to deliver its first row
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -66,25 +72,47 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        parsed = []
         for r in self.rows:
             try:
-                sm.append(float(r[1]))
-                mx = float(r[2])
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                parsed.append((ts, float(r[1]), float(r[2]), r))
             except Exception:
                 continue
+        pad = datetime.timedelta(milliseconds=30)
+        inside = [p for p in parsed if self.t0 is not None and self.t1 is not None and self.t0 - pad <= p[0] <= self.t1 + pad]
+        where = "timed region"
+        if not inside and parsed and self.t1 is not None:
+            # region shorter than the sampling period: the samples closest to it (the GPU is under the same load in the warm-up)
+            inside = sorted(parsed, key=lambda p: abs((p[0] - self.t1).total_seconds()))[:3]
+            where = "nearest samples (region shorter than the 50 ms sampling period)"
+        sm = [p[1] for p in inside]
+        mx = inside[-1][2] if inside else None
+        reasons = set()
+        for p in inside:
+            r = p[3]
             for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 def make_scene(N):
@@ -179,16 +207,18 @@ def run_ensemble(args, rank, world, local_rank, torch, dist, admm_b200):
         for s in sims:
             s.sync()
 
-    run(args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    run(args.warmup)
+    barrier()
     l0 = sum(s.info()["launches_total"] for s in sims)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     ev0.record()                       # idle stream: completes at once -> a device timestamp of "now"
     run(args.steps)                    # the timed region: K frames of every scene of this rank
     ev1.record()
     torch.cuda.synchronize()
+    sampler.end()
     ms_region = ev0.elapsed_time(ev1)
     l1 = sum(s.info()["launches_total"] for s in sims)
     clocks = sampler.stop()
@@ -294,12 +324,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident path: `value` -----------------------------------------------------------------------------
-    sim.step_resident(frames=args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sim.step_resident(frames=args.warmup)
+    barrier()
     l0 = sim.info()["launches_total"]
+    sampler.begin()
     sim.step_resident(frames=args.steps)      # the timed region: K frames, CUDA events on the library's stream
+    sampler.end()
     ms_region = sim.last_region_ms()
     l1 = sim.info()["launches_total"]
     barrier()
