@@ -41,6 +41,7 @@ def lib():
         L.oracle_num_hyper.argtypes = [_vp]
         L.oracle_get_prox.argtypes = [_vp, _vp, _vp]
         L.oracle_step.argtypes = [_vp, C.c_int, _dp, _dp, _vp, _vp, _vp, _vp]
+        L.oracle_local_step.argtypes = [_vp, _dp, _dp, _vp, _dp, _dp, _vp]
         _lib = L
     return _lib
 
@@ -137,6 +138,14 @@ class PortAdapter:
     def step(self):
         self.L.oracle_step(self.h, self.iters, self.x, self.v, None, None, None, None)
         return self.x.copy(), self.v.copy()
+
+    def local_step(self, x, u, prox=None):
+        """Teacher-forced half iteration: (z, u, optimiser state) of the local step on curr_x = x from the given u / state."""
+        z, uo = np.zeros(self.rows), np.zeros(self.rows)
+        po = np.zeros((self.nh, 4))
+        pin = None if (prox is None or not self.nh) else _f64(prox).ctypes.data_as(_vp)
+        self.L.oracle_local_step(self.h, _f64(x).reshape(-1), _f64(u).reshape(-1), pin, z, uo, po.ctypes.data_as(_vp) if self.nh else None)
+        return z, uo, po
 
     def prox_state(self):
         out = np.zeros((self.nh, 4))

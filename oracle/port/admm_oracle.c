@@ -4,7 +4,9 @@
  * admm::System::initialize()/step() and every Force::project, each function citing the reference file:line it
  * follows (A/ = /root/reference/deps/admm-elastic-sca).  It exists so that a checker is available where the
  * unmodified reference (oracle/_ref, built from /root/reference) is not; it is pinned against the reference's
- * golden dumps by tests/test_oracle_port.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+ * golden dumps by tests/test_oracle_port.py: replayed from the reference's own inputs, the local step of every golden
+ * iteration (z, u, optimiser state; all forces but FungTriangle, which is not restated here) is BIT-EXACT; free-running,
+ * x agrees to rounding where the reference is reproducible and within its own sensitivity where it is not.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
  * leg may load it.  Nothing here is shared with the product's csrc/ (written separately on purpose).
  */
 #include <float.h>
@@ -382,21 +384,81 @@ static void project_tet(force_t *f, const double *q, double *z) {
 		usvt(U, x2, V, z);
 	}
 }
-/* 3x2: polar factor / singular triplets through the symmetric 2x2 eigen-problem of F^T F (the reference uses
- * JacobiSVD<3x2>; the quantities used below, U(:,0:2) V^T and U diag(f(S)) V^T, do not depend on the SVD gauge) */
+/* 3x2: Eigen 3.2.5 JacobiSVD<Matrix<double,3,2>>(F, ComputeFullU | ComputeFullV), step by step: scaling
+ * (JacobiSVD.h:839-846), column-pivoting Householder QR preconditioner (QR/ColPivHouseholderQR.h:430-508 with
+ * Householder/Householder.h:60-130; U = householderQ, HouseholderSequence.h:236-277; V = column permutation), the 2x2
+ * Jacobi step on R (JacobiSVD.h:414-441, Jacobi.h:83-113), sign fix, sort, unscale (:899-929).  U here is its first two
+ * columns (all the triangle forces use).  q: column-major 3x2. */
 static void svd32(const double *q, double U[3][2], double S[2], double V[2][2]) {
-	double a = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], b = q[0] * q[3] + q[1] * q[4] + q[2] * q[5], c = q[3] * q[3] + q[4] * q[4] + q[5] * q[5];
-	double th = 0.5 * atan2(2.0 * b, a - c), cs = cos(th), sn = sin(th), l0, l1;
-	int r, k;
-	V[0][0] = cs; V[1][0] = sn; V[0][1] = -sn; V[1][1] = cs;
-	l0 = a * cs * cs + 2.0 * b * cs * sn + c * sn * sn;
-	l1 = a * sn * sn - 2.0 * b * cs * sn + c * cs * cs;
-	if (l1 > l0) { double t = l0; l0 = l1; l1 = t; V[0][0] = -sn; V[1][0] = cs; V[0][1] = cs; V[1][1] = sn; }
-	S[0] = sqrt(mx(l0, 0.0)); S[1] = sqrt(mx(l1, 0.0));
-	for (k = 0; k < 2; ++k) for (r = 0; r < 3; ++r) {
-		double fv = q[r] * V[0][k] + q[3 + r] * V[1][k];
-		U[r][k] = (S[k] > 0.0) ? fv / S[k] : (r == k ? 1.0 : 0.0);
+	double A[6], scale = 0.0, n0, n1, tau0, beta0, e00, e01, tau1, beta1, e10, Q[3][3], W[2][2], tmp;
+	int i, r, c, swapped, guard = 0;
+	for (i = 0; i < 6; ++i) if (fabs(q[i]) > scale) scale = fabs(q[i]);
+	if (scale == 0.0) scale = 1.0;
+	for (i = 0; i < 6; ++i) A[i] = q[i] / scale;
+	n0 = A[0] * A[0] + (A[1] * A[1] + A[2] * A[2]);     /* fixed-size column norms: a0 + (a1 + a2) */
+	n1 = A[3] * A[3] + (A[4] * A[4] + A[5] * A[5]);
+	swapped = n1 > n0;                                  /* first maximum wins */
+	if (swapped) for (r = 0; r < 3; ++r) { double t = A[r]; A[r] = A[3 + r]; A[3 + r] = t; }
+	{ /* k = 0 */
+		double c0 = A[0], tail = A[1] * A[1] + A[2] * A[2];
+		if (tail == 0.0) { tau0 = 0.0; beta0 = c0; e00 = e01 = 0.0; }
+		else { beta0 = sqrt(c0 * c0 + tail); if (c0 >= 0.0) beta0 = -beta0; e00 = A[1] / (c0 - beta0); e01 = A[2] / (c0 - beta0); tau0 = (beta0 - c0) / beta0; }
+		tmp = e00 * A[4] + e01 * A[5]; tmp += A[3];
+		A[3] -= tau0 * tmp; A[4] -= (tau0 * e00) * tmp; A[5] -= (tau0 * e01) * tmp;
 	}
+	{ /* k = 1 */
+		double c0 = A[4], tail = A[5] * A[5];
+		if (tail == 0.0) { tau1 = 0.0; beta1 = c0; e10 = 0.0; }
+		else { beta1 = sqrt(c0 * c0 + tail); if (c0 >= 0.0) beta1 = -beta1; e10 = A[5] / (c0 - beta1); tau1 = (beta1 - c0) / beta1; }
+	}
+	for (r = 0; r < 3; ++r) for (c = 0; c < 3; ++c) Q[r][c] = (r == c);
+	for (c = 1; c < 3; ++c) { tmp = e10 * Q[2][c]; tmp += Q[1][c]; Q[1][c] -= tau1 * tmp; Q[2][c] -= (tau1 * e10) * tmp; }
+	for (c = 0; c < 3; ++c) { tmp = e00 * Q[1][c] + e01 * Q[2][c]; tmp += Q[0][c]; Q[0][c] -= tau0 * tmp; Q[1][c] -= (tau0 * e00) * tmp; Q[2][c] -= (tau0 * e01) * tmp; }
+	W[0][0] = beta0; W[1][0] = 0.0; W[0][1] = A[3]; W[1][1] = beta1;
+	V[0][0] = swapped ? 0.0 : 1.0; V[1][0] = swapped ? 1.0 : 0.0; V[0][1] = swapped ? 1.0 : 0.0; V[1][1] = swapped ? 0.0 : 1.0;
+	while (guard++ < 64) { /* pair (p, q) = (1, 0) */
+		double thr = fmax(2.0 * 4.9406564584124654e-324, 2.0 * DBL_EPSILON * fmax(fabs(W[1][1]), fabs(W[0][0])));
+		double m00, m01, m10, m11, t, d, c1, s1, cr, sr, cl, sl, x, y;
+		if (!(fabs(W[1][0]) > thr || fabs(W[0][1]) > thr)) break;
+		m00 = W[1][1]; m01 = W[1][0]; m10 = W[0][1]; m11 = W[0][0];
+		t = m00 + m11; d = m10 - m01;
+		if (t == 0.0) { c1 = 0.0; s1 = d > 0.0 ? 1.0 : -1.0; }
+		else { double h = hyp(t, d); c1 = fabs(t) / h; s1 = d / h; if (t < 0.0) s1 = -s1; }
+		if (!(c1 == 1.0 && s1 == 0.0)) {
+			x = m00; y = m10; m00 = c1 * x + s1 * y; m10 = -s1 * x + c1 * y;
+			x = m01; y = m11; m01 = c1 * x + s1 * y; m11 = -s1 * x + c1 * y;
+		}
+		if (m01 == 0.0) { cr = 1.0; sr = 0.0; }
+		else {
+			double tau = (m00 - m11) / (2.0 * fabs(m01)), w = sqrt(tau * tau + 1.0), tt, n;
+			tt = (tau > 0.0) ? 1.0 / (tau + w) : 1.0 / (tau - w);
+			n = 1.0 / sqrt(tt * tt + 1.0);
+			sr = -(tt > 0.0 ? 1.0 : -1.0) * (m01 / fabs(m01)) * fabs(tt) * n;
+			cr = n;
+		}
+		cl = c1 * cr - s1 * (-sr);
+		sl = c1 * (-sr) + s1 * cr;
+		if (!(cl == 1.0 && sl == 0.0)) { /* rows 1, 0 of W; columns 1, 0 of Q */
+			for (c = 0; c < 2; ++c) { x = W[1][c]; y = W[0][c]; W[1][c] = cl * x + sl * y; W[0][c] = -sl * x + cl * y; }
+			for (r = 0; r < 3; ++r) { x = Q[r][1]; y = Q[r][0]; Q[r][1] = cl * x + sl * y; Q[r][0] = -sl * x + cl * y; }
+		}
+		if (!(cr == 1.0 && -sr == 0.0)) { /* columns 1, 0 of W and V with (c, s) = (cr, -sr) */
+			for (r = 0; r < 2; ++r) { x = W[r][1]; y = W[r][0]; W[r][1] = cr * x + (-sr) * y; W[r][0] = -(-sr) * x + cr * y; }
+			for (r = 0; r < 2; ++r) { x = V[r][1]; y = V[r][0]; V[r][1] = cr * x + (-sr) * y; V[r][0] = -(-sr) * x + cr * y; }
+		}
+	}
+	for (i = 0; i < 2; ++i) {
+		double a = fabs(W[i][i]);
+		S[i] = a;
+		if (a != 0.0) { double f = W[i][i] / a; for (r = 0; r < 3; ++r) Q[r][i] *= f; }
+	}
+	if (S[1] > S[0]) {
+		double t = S[0]; S[0] = S[1]; S[1] = t;
+		for (r = 0; r < 3; ++r) { t = Q[r][0]; Q[r][0] = Q[r][1]; Q[r][1] = t; }
+		for (r = 0; r < 2; ++r) { t = V[r][0]; V[r][0] = V[r][1]; V[r][1] = t; }
+	}
+	S[0] *= scale; S[1] *= scale;
+	for (r = 0; r < 3; ++r) { U[r][0] = Q[r][0]; U[r][1] = Q[r][1]; }
 }
 static void project_tri(force_t *f, const double *q, double *z) {
 	double U[3][2], S[2], V[2][2], p[6];
@@ -672,10 +734,76 @@ static void wind(const oracle_sys *S, const double *x, double *v) { /* WindForce
 	}
 }
 
+/* The local step of one ADMM iteration (System.cpp:54-58) and, if b != NULL, this iteration's share of the right-hand
+ * side (System.cpp:61).  Dx sums a row's terms in ascending node index: Eigen's column-major m_D * curr_x visits the
+ * columns in that order (SparseDenseProduct.h:190-209). */
+static void local_pass(oracle_sys *S, const double *cx, double *b) {
+	int n = S->n, e, i, j, k, c, r;
+	double dt2 = S->dt * S->dt;
+	for (e = 0; e < S->nf; ++e) {
+		force_t *f = &S->f[e];
+		double sel[3][4], Dx[9], q[9], z[9], *u = S->u + f->row, cw = dt2 * f->w * f->w;
+		int nr = selector(f, sel), ord[4], a, t;
+		for (c = 0; c < f->nv; ++c) ord[c] = c;
+		for (a = 1; a < f->nv; ++a) { t = ord[a]; c = a - 1; while (c >= 0 && f->idx[ord[c]] > f->idx[t]) { ord[c + 1] = ord[c]; --c; } ord[c + 1] = t; }
+		for (r = 0; r < nr; ++r) for (j = 0; j < 3; ++j) {
+			double s = 0.0;
+			int first = 1;
+			for (a = 0; a < f->nv; ++a) {
+				c = ord[a];
+				if (sel[r][c] == 0.0) continue;           /* structural zeros are not stored in m_D */
+				if (first) { s = sel[r][c] * cx[3 * f->idx[c] + j]; first = 0; }
+				else s += sel[r][c] * cx[3 * f->idx[c] + j];
+			}
+			Dx[3 * r + j] = s;
+		}
+		for (k = 0; k < f->rows; ++k) q[k] = Dx[k] + u[k];
+		switch (f->type) {
+		case F_TET: project_tet(f, q, z); break;
+		case F_TRI: project_tri(f, q, z); break;
+		case F_SPRING: project_spring(f, q, z); break;
+		case F_BEND: project_bend(f, q, z); break;
+		case F_SANCHOR: memcpy(z, f->aux, 3 * sizeof(double)); break;                 /* AnchorForce.cpp:46-55 */
+		default: /* MovingAnchor::project AnchorForce.cpp:71-89 */
+			if (f->active) memcpy(z, f->aux, 3 * sizeof(double));
+			else { for (k = 0; k < 3; ++k) { z[k] = q[k]; f->aux[k] = Dx[k]; } }
+		}
+		for (k = 0; k < f->rows; ++k) { u[k] = u[k] + (Dx[k] - z[k]); S->z[f->row + k] = z[k]; }
+		if (b) for (r = 0; r < nr; ++r) for (j = 0; j < 3; ++j) { /* b += dt^2 D^T W^2 (z - u), System.cpp:61 */
+			double zu = z[3 * r + j] - u[3 * r + j];
+			for (c = 0; c < f->nv; ++c) b[3 * f->idx[c] + j] += cw * sel[r][c] * zu;
+		}
+	}
+	if (S->has_coll) { /* CollisionForce::project CollisionForce.cpp:36-46 */
+		double cw = dt2 * S->coll_w * S->coll_w;
+		for (i = 0; i < n; ++i) {
+			double *u = S->u + S->coll_row + 3 * i, p[3];
+			for (j = 0; j < 3; ++j) p[j] = cx[3 * i + j] + u[j];
+			collide(S, p);
+			for (j = 0; j < 3; ++j) { u[j] = u[j] + (cx[3 * i + j] - p[j]); S->z[S->coll_row + 3 * i + j] = p[j]; if (b) b[3 * i + j] += cw * (p[j] - u[j]); }
+		}
+	}
+}
+
+/* Teacher-forced half iteration for the parity tests: u (and the hyperelastic optimiser state, 4 per tet, may be NULL) are
+ * set, the local step runs on curr_x = x, and z, u and the new optimiser state are returned. */
+int oracle_local_step(oracle_sys *S, const double *x, const double *u_in, const double *prox_in, double *z_out, double *u_out, double *prox_out) {
+	int e, c = 0;
+	memcpy(S->u, u_in, sizeof(double) * S->rows);
+	if (prox_in) for (e = 0; e < S->nf; ++e) if (S->f[e].type == F_TET && (S->f[e].kind == 1 || S->f[e].kind == 2)) {
+		memcpy(S->f[e].prox, prox_in + 4 * c, 3 * sizeof(double)); S->f[e].init_hess = prox_in[4 * c + 3]; ++c;
+	}
+	local_pass(S, x, 0);
+	memcpy(z_out, S->z, sizeof(double) * S->rows);
+	memcpy(u_out, S->u, sizeof(double) * S->rows);
+	if (prox_out) oracle_get_prox(S, prox_out, 0);
+	return 0;
+}
+
 /* System::step (System.cpp:26-75).  x_it/z_it/u_it (optional): per-iteration dumps in the layout of oracle/ref_shim.cpp */
 int oracle_step(oracle_sys *S, int iters, double *x, double *v, double *x_it, double *z_it, double *u_it, double *prox_it) {
-	int n = S->n, n3 = 3 * n, it, e, i, j, k, c, r, g;
-	double dt = S->dt, dt2 = dt * dt, *xbar = (double *)malloc(sizeof(double) * n3), *cx = (double *)malloc(sizeof(double) * n3), *b = (double *)malloc(sizeof(double) * n3);
+	int n = S->n, n3 = 3 * n, it, i, j, k, g;
+	double dt = S->dt, *xbar = (double *)malloc(sizeof(double) * n3), *cx = (double *)malloc(sizeof(double) * n3), *b = (double *)malloc(sizeof(double) * n3);
 	int nh = oracle_num_hyper(S);
 	if (S->wind_tris && !S->wind_after_gravity) wind(S, x, v);
 	for (g = 0; g < S->ngrav; ++g) for (i = 0; i < n; ++i) for (j = 0; j < 3; ++j) v[3 * i + j] += (dt * S->grav[g][j]);
@@ -684,41 +812,7 @@ int oracle_step(oracle_sys *S, int iters, double *x, double *v, double *x_it, do
 	for (it = 0; it < iters; ++it) {
 		if (x_it) memcpy(x_it + (size_t)it * n3, cx, sizeof(double) * n3);
 		for (i = 0; i < n3; ++i) b[i] = S->m[i / 3] * xbar[i];
-		for (e = 0; e < S->nf; ++e) {
-			force_t *f = &S->f[e];
-			double sel[3][4], Dx[9], q[9], z[9], *u = S->u + f->row, cw = dt2 * f->w * f->w;
-			int nr = selector(f, sel);
-			for (r = 0; r < nr; ++r) for (j = 0; j < 3; ++j) {
-				double s = 0.0;
-				for (c = 0; c < f->nv; ++c) s += sel[r][c] * cx[3 * f->idx[c] + j];
-				Dx[3 * r + j] = s;
-			}
-			for (k = 0; k < f->rows; ++k) q[k] = Dx[k] + u[k];
-			switch (f->type) {
-			case F_TET: project_tet(f, q, z); break;
-			case F_TRI: project_tri(f, q, z); break;
-			case F_SPRING: project_spring(f, q, z); break;
-			case F_BEND: project_bend(f, q, z); break;
-			case F_SANCHOR: memcpy(z, f->aux, 3 * sizeof(double)); break;                 /* AnchorForce.cpp:46-55 */
-			default: /* MovingAnchor::project AnchorForce.cpp:71-89 */
-				if (f->active) memcpy(z, f->aux, 3 * sizeof(double));
-				else { for (k = 0; k < 3; ++k) { z[k] = q[k]; f->aux[k] = Dx[k]; } }
-			}
-			for (k = 0; k < f->rows; ++k) { u[k] = u[k] + (Dx[k] - z[k]); S->z[f->row + k] = z[k]; }
-			for (r = 0; r < nr; ++r) for (j = 0; j < 3; ++j) { /* b += dt^2 D^T W^2 (z - u), System.cpp:61 */
-				double zu = z[3 * r + j] - u[3 * r + j];
-				for (c = 0; c < f->nv; ++c) b[3 * f->idx[c] + j] += cw * sel[r][c] * zu;
-			}
-		}
-		if (S->has_coll) { /* CollisionForce::project CollisionForce.cpp:36-46 */
-			double cw = dt2 * S->coll_w * S->coll_w;
-			for (i = 0; i < n; ++i) {
-				double *u = S->u + S->coll_row + 3 * i, p[3];
-				for (j = 0; j < 3; ++j) p[j] = cx[3 * i + j] + u[j];
-				collide(S, p);
-				for (j = 0; j < 3; ++j) { u[j] = u[j] + (cx[3 * i + j] - p[j]); S->z[S->coll_row + 3 * i + j] = p[j]; b[3 * i + j] += cw * (p[j] - u[j]); }
-			}
-		}
+		local_pass(S, cx, b);
 		if (z_it) memcpy(z_it + (size_t)it * S->rows, S->z, sizeof(double) * S->rows);
 		if (u_it) memcpy(u_it + (size_t)it * S->rows, S->u, sizeof(double) * S->rows);
 		if (prox_it && nh) oracle_get_prox(S, prox_it + (size_t)it * nh * 4, 0);

@@ -64,6 +64,41 @@ def test_port_against_reference_golden(name):
     assert ok, "; ".join(report)
 
 
+@pytest.mark.parametrize("name", list(SCEN))
+def test_port_local_step_is_bit_exact_teacher_forced(name):
+    """The restatement is literal: replayed from the reference's own inputs (x entering the iteration, u and optimiser
+    state of the previous one), every ADMM iteration's z, u and optimiser state come out bit for bit."""
+    port = _port()
+    if name == "cloth_fung":
+        pytest.skip("FungTriangle is not restated in the C port")
+    gold = np.load(os.path.join(GOLDEN, f"{name}.ref.npz"))
+    scenario = dict(SCEN[name])
+    scenario["scene"] = scenes.load_scene(os.path.join(GOLDEN, f"{name}.scene.npz"))
+    ad = port.PortAdapter(scenario["scene"])
+    F, K = gold["x_it"].shape[:2]
+    R = gold["z_it"].shape[2]
+    has_prox = "prox_it" in gold.files and gold["prox_it"].size > 0
+    u_prev = np.zeros(R)
+    prox_prev = np.ones(gold["prox_it"].shape[2:]) if has_prox else None
+    ev = scenario.get("events")
+    n_exact = n_total = 0
+    for f in range(F):
+        if ev is not None:
+            ev(f, ad)
+        for k in range(K):
+            z, u, p = ad.local_step(gold["x_it"][f, k], u_prev, prox_prev)
+            ok = np.array_equal(z, gold["z_it"][f, k]) and np.array_equal(u, gold["u_it"][f, k])
+            if has_prox:
+                ok = ok and np.array_equal(p, gold["prox_it"][f, k])
+                prox_prev = gold["prox_it"][f, k]
+            n_total += 1
+            n_exact += int(ok)
+            u_prev = gold["u_it"][f, k]
+    ad.close()
+    print(f"{name}: port local step bit-exact in {n_exact}/{n_total} iterations")
+    assert n_exact == n_total
+
+
 def test_reference_library_known_answers_when_present():
     from oracle import ref
     if not ref.available():
