@@ -31,6 +31,7 @@ extern "C" int admmb_create(int device, admmb_ctx **out) {
 	admmb_ctx *ctx = new admmb_ctx();
 	ctx->device = device;
 	if (getenv("ADMMB_NO_GRAPH")) ctx->use_graph = false;
+	if (const char *e = getenv("ADMMB_DETERMINISTIC")) ctx->deterministic = e[0] && e[0] != '0';
 	e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ADMMB_E_CUDA; }
 	*out = ctx;
@@ -219,6 +220,12 @@ extern "C" int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *i
 extern "C" int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3) {
 	if (!ctx) return ADMMB_E_ARG;
 	return add_explicit(ctx, 2, ntris, tris3, 3, dir3, "wind");
+}
+
+extern "C" int admmb_set_deterministic(admmb_ctx *ctx, int on) {
+	CHECK_BUILDING(ctx);
+	ctx->deterministic = on != 0;
+	return ADMMB_OK;
 }
 
 extern "C" int admmb_set_host_threads(int n) {

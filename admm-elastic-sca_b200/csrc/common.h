@@ -156,6 +156,7 @@ struct admmb_ctx {
 	int dist_rank = 0, dist_world = 1;
 	int own0 = 0, own1 = 0, chunk = 0;  // chunk = ceil(n / world); node vectors are allocated world * chunk long
 	void *nccl_comm = nullptr;
+	bool deterministic = false; // admmb_set_deterministic: atomic-free (bit-reproducible) direct solve
 	bool use_graph = true;
 	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)
 	cudaGraphExec_t iter_graph_exec = nullptr;

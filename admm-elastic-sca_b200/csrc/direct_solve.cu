@@ -55,6 +55,12 @@ struct DirectSolver {
 	int unroll = 16; // loads in flight per thread of the per-level kernel (ADMMB_SOLVE_UNROLL = 8 | 16 | 32)
 	int slots = 0;   // resident CTAs of the per-level kernel on the whole device
 	int split = 0;   // ADMMB_SOLVE_SPLIT: 0 = choose per level, else log2 of the forced column split + 1
+	// bit-reproducible variant (ctx->deterministic): tiles store their partial sums, a second kernel per level adds them
+	// to the vectors in a fixed order (no floating-point atomics)
+	bool det = false;
+	DevBuf<double> d_part;                 // [3][rows of the widest phase]
+	DevBuf<int> d_red_key, d_red_ptr, d_red_slot; // per phase: targets (vector id * n + row), CSR into the slot list
+	std::vector<int> red_first, red_count; // per phase: range of targets
 };
 
 // fire-and-forget FP64 add at L2 (RED.E.ADD.F64): the generic atomicAdd would also emit a shared-memory CAS path
@@ -174,6 +180,81 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level_pf(const SolveTile *__re
 	red_add(vout + 3 * (size_t)go + 0, a0);
 	red_add(vout + 3 * (size_t)go + 1, a1);
 	red_add(vout + 3 * (size_t)go + 2, a2);
+}
+
+// Bit-reproducible variant: the tile's partial sums go to its own rows of `part` instead of being added atomically; the
+// additions then happen in k_solve_reduce in a fixed order.  (t.pad = first partial row of the tile within its phase.)
+template <int UNROLL>
+__global__ void __launch_bounds__(TILE_R) k_solve_level_det(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
+                                                            const int *__restrict__ pool, const double *vb, const double *vy, const double *vx,
+                                                            double *__restrict__ part) {
+	const SolveTile t = tiles[blockIdx.x];
+	__shared__ double sv[TILE_C][3];
+	const int r = threadIdx.x;
+	const bool active = r < t.nrows;
+	const int ld = t.nrows;
+	const double *M = data + t.off + (active ? r : 0);
+	double m[UNROLL];
+#pragma unroll
+	for (int k = 0; k < UNROLL; ++k) m[k] = (active && k < t.ncols) ? __ldcs(M + (size_t)k * ld) : 0.0;
+	const int si = (t.flags >> TF_IN_SHIFT) & 3;
+	const double *vin = si == 0 ? vb : (si == 1 ? vy : vx);
+	for (int c = threadIdx.x; c < TILE_C; c += TILE_R) {
+		if (c < t.ncols) {
+			const int gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c] : t.in_idx + c;
+			sv[c][0] = vin[3 * (size_t)gi + 0];
+			sv[c][1] = vin[3 * (size_t)gi + 1];
+			sv[c][2] = vin[3 * (size_t)gi + 2];
+		} else {
+			sv[c][0] = 0.0; sv[c][1] = 0.0; sv[c][2] = 0.0;
+		}
+	}
+	__syncthreads();
+	if (!active) return;
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+	for (int k = 0; k < UNROLL; ++k) {
+		a0 += m[k] * sv[k][0];
+		a1 += m[k] * sv[k][1];
+		a2 += m[k] * sv[k][2];
+	}
+	int c = UNROLL;
+	for (; c + UNROLL <= t.ncols; c += UNROLL) {
+#pragma unroll
+		for (int k = 0; k < UNROLL; ++k) m[k] = __ldcs(M + (size_t)(c + k) * ld);
+#pragma unroll
+		for (int k = 0; k < UNROLL; ++k) {
+			a0 += m[k] * sv[c + k][0];
+			a1 += m[k] * sv[c + k][1];
+			a2 += m[k] * sv[c + k][2];
+		}
+	}
+	for (; c < t.ncols; ++c) {
+		const double mm = __ldcs(M + (size_t)c * ld);
+		a0 += mm * sv[c][0];
+		a1 += mm * sv[c][1];
+		a2 += mm * sv[c][2];
+	}
+	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
+	double *p = part + 3 * ((size_t)t.pad + r);
+	p[0] = a0; p[1] = a1; p[2] = a2;
+}
+
+// one thread per target row of the phase: v[row] += sum of its partial rows, in ascending slot order
+__global__ void __launch_bounds__(256) k_solve_reduce(int count, int n, const int *__restrict__ key, const int *__restrict__ ptr,
+                                                      const int *__restrict__ slot, const double *__restrict__ part, double *vb, double *vy,
+                                                      double *vx) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= count) return;
+	const int kk = key[j], vec = kk / n, row = kk - vec * n;
+	double *v = (vec == 0 ? vb : (vec == 1 ? vy : vx)) + 3 * (size_t)row;
+	double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+	const int p1 = ptr[j + 1];
+	for (int p = ptr[j]; p < p1; ++p) {
+		const double *q = part + 3 * (size_t)slot[p];
+		s0 += q[0]; s1 += q[1]; s2 += q[2];
+	}
+	v[0] += s0; v[1] += s1; v[2] += s2;
 }
 
 // Same tile product, launched once per level with PROGRAMMATIC DEPENDENT LAUNCH: every CTA first releases the next
@@ -534,6 +615,48 @@ int direct_setup(admmb_ctx *ctx) {
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(S.d_data.p, packed.get(), (S.data_doubles + 16) * sizeof(double), cudaMemcpyHostToDevice, s));
 	std::vector<SolveTile> all(ftiles);
 	all.insert(all.end(), btiles.begin(), btiles.end());
+	S.det = ctx->deterministic;
+	if (S.det) {
+		// phases: forward levels ascending, backward levels descending (the order direct_solve walks them)
+		const int nl = F.nlevels;
+		std::vector<int> key, ptr(1, 0), slot;
+		S.red_first.assign(2 * nl, 0);
+		S.red_count.assign(2 * nl, 0);
+		size_t max_rows = 1;
+		std::vector<std::pair<int, int> > pairs; // (target key, partial row)
+		for (int ph = 0; ph < 2 * nl; ++ph) {
+			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
+			const int first = ph < nl ? f_first[lv] : (int)ftiles.size() + b_first[lv];
+			const int cnt = ph < nl ? f_count[lv] : b_count[lv];
+			pairs.clear();
+			int rows = 0;
+			for (int i = first; i < first + cnt; ++i) {
+				SolveTile &t = all[i];
+				t.pad = rows;
+				const int vec = (t.flags >> TF_OUT_SHIFT) & 3;
+				for (int r = 0; r < t.nrows; ++r) {
+					const int go = (t.flags & TF_OUT_LIST) ? F.rows[t.out_idx + r] : t.out_idx + r;
+					pairs.push_back(std::make_pair(vec * ctx->n + go, rows + r));
+				}
+				rows += t.nrows;
+			}
+			max_rows = std::max<size_t>(max_rows, rows);
+			std::sort(pairs.begin(), pairs.end());
+			S.red_first[ph] = (int)key.size();
+			for (size_t q = 0; q < pairs.size(); ++q) {
+				if (q == 0 || pairs[q].first != pairs[q - 1].first) { key.push_back(pairs[q].first); ptr.push_back((int)slot.size()); }
+				slot.push_back(pairs[q].second);
+				ptr.back() = (int)slot.size();
+			}
+			S.red_count[ph] = (int)key.size() - S.red_first[ph];
+		}
+		// ptr holds, for target j, the END of its slot range at ptr[j + 1] (ptr[0] = 0)
+		ADMMB_CUDA(ctx, S.d_part.alloc(3 * max_rows));
+		ADMMB_CUDA(ctx, S.d_red_key.upload(key, ctx->stream));
+		ADMMB_CUDA(ctx, S.d_red_ptr.upload(ptr, ctx->stream));
+		ADMMB_CUDA(ctx, S.d_red_slot.upload(slot, ctx->stream));
+		ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
 	ADMMB_CUDA(ctx, S.d_tiles.alloc(std::max<size_t>(all.size(), 1)));
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(S.d_tiles.p, all.data(), all.size() * sizeof(SolveTile), cudaMemcpyHostToDevice, s));
 	ADMMB_CUDA(ctx, S.d_pool.alloc(std::max<size_t>(F.rows.size(), 1)));
@@ -589,7 +712,7 @@ int direct_solve(admmb_ctx *ctx) {
 	const size_t bytes = 3 * (size_t)ctx->n * sizeof(double);
 	ADMMB_CUDA(ctx, cudaMemsetAsync(S.d_y.p, 0, S.d_y.bytes(), s)); // y and the phase barrier counters behind it
 	ADMMB_CUDA(ctx, cudaMemsetAsync(ctx->d_currx.p, 0, bytes, s));
-	if (S.mode == 1) {
+	if (S.mode == 1 && !S.det) {
 		const int smem = PS_SMEM;
 		unsigned *gbar = reinterpret_cast<unsigned *>(S.d_y.p + 3 * (size_t)ctx->n);
 		k_solve_persistent<<<S.grid, PS_THREADS, smem, s>>>(S.d_tiles.p, S.d_data.p, S.d_pool.p, S.d_phase_first.p, S.d_phase_count.p,
@@ -599,7 +722,7 @@ int direct_solve(admmb_ctx *ctx) {
 		return ADMMB_OK;
 	}
 	const int nl = S.F.nlevels;
-	if (S.mode == 2) {
+	if (S.mode == 2 && !S.det) {
 		// launch per level, each launch (after the first) programmatically dependent on the previous one
 		bool first = true;
 		for (int ph = 0; ph < 2 * nl; ++ph) {
@@ -625,6 +748,16 @@ int direct_solve(admmb_ctx *ctx) {
 		const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
 		const SolveTile *tl = S.d_tiles.p + (ph < nl ? S.fwd_first[lv] : S.bwd_first[lv]);
 		if (cnt == 0) continue;
+		if (S.det) {
+			if (S.unroll == 32) k_solve_level_det<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
+			else if (S.unroll == 16) k_solve_level_det<16><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
+			else k_solve_level_det<8><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
+			const int rc = S.red_count[ph];
+			k_solve_reduce<<<(rc + 255) / 256, 256, 0, s>>>(rc, ctx->n, S.d_red_key.p + S.red_first[ph], S.d_red_ptr.p + S.red_first[ph],
+			                                                S.d_red_slot.p, S.d_part.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
+			ctx->launches += 2;
+			continue;
+		}
 		if (S.mode == 3) {
 			// column split: as long as twice the CTAs still fit the machine at once, halve the columns per CTA
 			int sl = 0;
@@ -647,6 +780,7 @@ void direct_destroy(admmb_ctx *ctx) {
 	if (!ctx->direct) return;
 	DirectSolver &S = *ctx->direct;
 	S.d_data.free(); S.d_tiles.free(); S.d_pool.free(); S.d_y.free(); S.d_phase_first.free(); S.d_phase_count.free(); S.d_err.free();
+	S.d_part.free(); S.d_red_key.free(); S.d_red_ptr.free(); S.d_red_slot.free();
 	delete ctx->direct;
 	ctx->direct = nullptr;
 }

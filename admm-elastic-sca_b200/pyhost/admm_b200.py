@@ -27,7 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
-    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic",
 ]
 
 
@@ -64,6 +64,7 @@ def lib():
     L.admmb_add_collision.argtypes = [vp, C.c_int, _ip, _dp, C.c_double]
     L.admmb_set_gravity.argtypes = [vp, C.c_int, _dp]
     L.admmb_set_host_threads.argtypes = [C.c_int]
+    L.admmb_set_deterministic.argtypes = [vp, C.c_int]
     L.admmb_register_host_buffer.argtypes = [vp, vp, C.c_long]
     L.admmb_download_x_f32.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]
     L.admmb_unregister_host_buffer.argtypes = [vp, vp]
@@ -118,7 +119,7 @@ class System:
     recompute_weights().  Built from a scene dictionary (scenes.py).
     """
 
-    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None, host_explicit=False, pin_host=False):
+    def __init__(self, scene, device=0, solver=SOLVER_DIRECT, cg_tol=1e-12, cg_max_iters=20000, iters=None, dist=None, host_explicit=False, pin_host=False, deterministic=None):
         """dist = (rank, world, id128 bytes) partitions the mesh over `world` processes (PCG only)."""
         L = lib()
         self.L = L
@@ -190,6 +191,8 @@ class System:
                     self._ck(gid)
                 self.gravity_ids.append(gid)
         self._ck(L.admmb_set_solver(h, int(solver), float(cg_tol), int(cg_max_iters)))
+        if deterministic is not None:
+            self._ck(L.admmb_set_deterministic(h, 1 if deterministic else 0))
         if dist is not None:
             self._ck(L.admmb_dist_init(h, int(dist[0]), int(dist[1]), dist[2]))
         self._ck(L.admmb_finalize(h, self.dt))

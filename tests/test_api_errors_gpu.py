@@ -148,3 +148,26 @@ def test_async_stepping_of_several_contexts_matches_sequential_stepping():
         s.download()
         assert np.abs(s.m_x - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
         s.close()
+
+
+def test_deterministic_solve_is_bit_reproducible_and_agrees_with_the_default():
+    """admmb_set_deterministic: two runs on the same input are bit-identical (the default accumulates the solve with
+    floating-point atomics, reproducible only to rounding), and both modes agree to rounding where the dynamics do not
+    amplify it (ARAP; the NeoHookean line search does)."""
+
+    def run(sc, det):
+        s = admm_b200.System(sc, deterministic=det)
+        s.set_x(sc["x_after_init"])
+        xs = []
+        for _ in range(4):
+            s.step()
+            xs.append(s.m_x.copy())
+        s.close()
+        return np.array(xs)
+
+    nh = scenes.cube_scene(8, kind=scenes.TET_NH, seed=3)
+    a, b = run(nh, True), run(nh, True)
+    assert np.array_equal(a, b), "deterministic mode is not bit-reproducible"
+    arap = scenes.cube_scene(8, kind=scenes.TET_ARAP, seed=3)
+    c, d = run(arap, True), run(arap, False)
+    assert np.abs(c - d).max() <= 1e-12 * np.abs(c).max()
