@@ -60,7 +60,8 @@ struct DirectSolver {
 	bool det = false;
 	DevBuf<double> d_part;                 // [3][rows of the widest phase]
 	DevBuf<int> d_red_key, d_red_ptr, d_red_slot; // per phase: targets (vector id * n + row), CSR into the slot list
-	std::vector<int> red_first, red_count; // per phase: range of targets
+	DevBuf<int> d_red_tgt, d_red_counter;  // partial row -> target (per phase, concatenated); arrivals per target
+	std::vector<int> red_first, red_count, red_row_first; // per phase: range of targets, first entry of d_red_tgt
 };
 
 // fire-and-forget FP64 add at L2 (RED.E.ADD.F64): the generic atomicAdd would also emit a shared-memory CAS path
@@ -182,12 +183,15 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level_pf(const SolveTile *__re
 	red_add(vout + 3 * (size_t)go + 2, a2);
 }
 
-// Bit-reproducible variant: the tile's partial sums go to its own rows of `part` instead of being added atomically; the
-// additions then happen in k_solve_reduce in a fixed order.  (t.pad = first partial row of the tile within its phase.)
+// Bit-reproducible variant: no floating-point atomics.  Every tile stores its partial sums in its own rows of `part`
+// (t.pad = first partial row of the tile within its phase); each output row of a phase has a counter of arrivals, and the
+// thread that completes it -- whichever tile that happens to be -- adds the row's partial sums to the vector in ASCENDING
+// partial-row order, i.e. always in the same order.  ("Last block reduces": partial stores, __threadfence, counter.)
 template <int UNROLL>
 __global__ void __launch_bounds__(TILE_R) k_solve_level_det(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
-                                                            const int *__restrict__ pool, const double *vb, const double *vy, const double *vx,
-                                                            double *__restrict__ part) {
+                                                            const int *__restrict__ pool, double *vb, double *vy, double *vx,
+                                                            double *part, const int *__restrict__ tgt_of_row, const int *__restrict__ tgt_key,
+                                                            const int *__restrict__ tgt_ptr, const int *__restrict__ tgt_slot, int *counter, int n) {
 	const SolveTile t = tiles[blockIdx.x];
 	__shared__ double sv[TILE_C][3];
 	const int r = threadIdx.x;
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level_det(const SolveTile *__r
 	double m[UNROLL];
 #pragma unroll
 	for (int k = 0; k < UNROLL; ++k) m[k] = (active && k < t.ncols) ? __ldcs(M + (size_t)k * ld) : 0.0;
+	const int tj = active ? tgt_of_row[t.pad + r] : 0; // target (output row of this phase) this partial row belongs to
 	const int si = (t.flags >> TF_IN_SHIFT) & 3;
 	const double *vin = si == 0 ? vb : (si == 1 ? vy : vx);
 	for (int c = threadIdx.x; c < TILE_C; c += TILE_R) {
@@ -236,23 +241,23 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level_det(const SolveTile *__r
 		a2 += mm * sv[c][2];
 	}
 	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
-	double *p = part + 3 * ((size_t)t.pad + r);
-	p[0] = a0; p[1] = a1; p[2] = a2;
-}
-
-// one thread per target row of the phase: v[row] += sum of its partial rows, in ascending slot order
-__global__ void __launch_bounds__(256) k_solve_reduce(int count, int n, const int *__restrict__ key, const int *__restrict__ ptr,
-                                                      const int *__restrict__ slot, const double *__restrict__ part, double *vb, double *vy,
-                                                      double *vx) {
-	const int j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= count) return;
-	const int kk = key[j], vec = kk / n, row = kk - vec * n;
+	const int p0 = tgt_ptr[tj], p1 = tgt_ptr[tj + 1];
+	const int kk = tgt_key[tj], vec = kk / n, row = kk - vec * n;
 	double *v = (vec == 0 ? vb : (vec == 1 ? vy : vx)) + 3 * (size_t)row;
+	if (p1 - p0 == 1) { // the only contribution to this row in this phase: nobody else touches it
+		v[0] += a0; v[1] += a1; v[2] += a2;
+		return;
+	}
+	double *p = part + 3 * ((size_t)t.pad + r);
+	__stcg(p + 0, a0); __stcg(p + 1, a1); __stcg(p + 2, a2);
+	__threadfence();
+	if (atomicAdd(counter + tj, 1) != p1 - p0 - 1) return;
+	__threadfence();
+	counter[tj] = 0; // ready for the next solve
 	double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-	const int p1 = ptr[j + 1];
-	for (int p = ptr[j]; p < p1; ++p) {
-		const double *q = part + 3 * (size_t)slot[p];
-		s0 += q[0]; s1 += q[1]; s2 += q[2];
+	for (int q = p0; q < p1; ++q) {
+		const double *pq = part + 3 * (size_t)tgt_slot[q];
+		s0 += __ldcg(pq + 0); s1 += __ldcg(pq + 1); s2 += __ldcg(pq + 2);
 	}
 	v[0] += s0; v[1] += s1; v[2] += s2;
 }
@@ -624,6 +629,8 @@ int direct_setup(admmb_ctx *ctx) {
 		S.red_count.assign(2 * nl, 0);
 		size_t max_rows = 1;
 		std::vector<std::pair<int, int> > pairs; // (target key, partial row)
+		std::vector<int> tgt_of_row;
+		S.red_row_first.assign(2 * nl, 0);
 		for (int ph = 0; ph < 2 * nl; ++ph) {
 			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
 			const int first = ph < nl ? f_first[lv] : (int)ftiles.size() + b_first[lv];
@@ -643,10 +650,14 @@ int direct_setup(admmb_ctx *ctx) {
 			max_rows = std::max<size_t>(max_rows, rows);
 			std::sort(pairs.begin(), pairs.end());
 			S.red_first[ph] = (int)key.size();
+			S.red_row_first[ph] = (int)tgt_of_row.size();
+			tgt_of_row.resize(tgt_of_row.size() + rows);
+			int *tor = tgt_of_row.data() + S.red_row_first[ph];
 			for (size_t q = 0; q < pairs.size(); ++q) {
 				if (q == 0 || pairs[q].first != pairs[q - 1].first) { key.push_back(pairs[q].first); ptr.push_back((int)slot.size()); }
 				slot.push_back(pairs[q].second);
 				ptr.back() = (int)slot.size();
+				tor[pairs[q].second] = (int)key.size() - 1 - S.red_first[ph]; // target index within the phase
 			}
 			S.red_count[ph] = (int)key.size() - S.red_first[ph];
 		}
@@ -655,6 +666,9 @@ int direct_setup(admmb_ctx *ctx) {
 		ADMMB_CUDA(ctx, S.d_red_key.upload(key, ctx->stream));
 		ADMMB_CUDA(ctx, S.d_red_ptr.upload(ptr, ctx->stream));
 		ADMMB_CUDA(ctx, S.d_red_slot.upload(slot, ctx->stream));
+		ADMMB_CUDA(ctx, S.d_red_tgt.upload(tgt_of_row, ctx->stream));
+		ADMMB_CUDA(ctx, S.d_red_counter.alloc(std::max<size_t>(key.size(), 1)));
+		ADMMB_CUDA(ctx, S.d_red_counter.zero(ctx->stream));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
 	ADMMB_CUDA(ctx, S.d_tiles.alloc(std::max<size_t>(all.size(), 1)));
@@ -749,13 +763,12 @@ int direct_solve(admmb_ctx *ctx) {
 		const SolveTile *tl = S.d_tiles.p + (ph < nl ? S.fwd_first[lv] : S.bwd_first[lv]);
 		if (cnt == 0) continue;
 		if (S.det) {
-			if (S.unroll == 32) k_solve_level_det<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
-			else if (S.unroll == 16) k_solve_level_det<16><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
-			else k_solve_level_det<8><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p);
-			const int rc = S.red_count[ph];
-			k_solve_reduce<<<(rc + 255) / 256, 256, 0, s>>>(rc, ctx->n, S.d_red_key.p + S.red_first[ph], S.d_red_ptr.p + S.red_first[ph],
-			                                                S.d_red_slot.p, S.d_part.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
-			ctx->launches += 2;
+			const int *tor = S.d_red_tgt.p + S.red_row_first[ph], *tk = S.d_red_key.p + S.red_first[ph], *tp = S.d_red_ptr.p + S.red_first[ph];
+			int *cn = S.d_red_counter.p + S.red_first[ph];
+			if (S.unroll == 32) k_solve_level_det<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p, tor, tk, tp, S.d_red_slot.p, cn, ctx->n);
+			else if (S.unroll == 16) k_solve_level_det<16><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p, tor, tk, tp, S.d_red_slot.p, cn, ctx->n);
+			else k_solve_level_det<8><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, S.d_part.p, tor, tk, tp, S.d_red_slot.p, cn, ctx->n);
+			ctx->launches++;
 			continue;
 		}
 		if (S.mode == 3) {
@@ -780,7 +793,7 @@ void direct_destroy(admmb_ctx *ctx) {
 	if (!ctx->direct) return;
 	DirectSolver &S = *ctx->direct;
 	S.d_data.free(); S.d_tiles.free(); S.d_pool.free(); S.d_y.free(); S.d_phase_first.free(); S.d_phase_count.free(); S.d_err.free();
-	S.d_part.free(); S.d_red_key.free(); S.d_red_ptr.free(); S.d_red_slot.free();
+	S.d_part.free(); S.d_red_key.free(); S.d_red_ptr.free(); S.d_red_slot.free(); S.d_red_tgt.free(); S.d_red_counter.free();
 	delete ctx->direct;
 	ctx->direct = nullptr;
 }

@@ -105,8 +105,8 @@ int admmb_set_host_threads(int n);
 /* Bit-reproducible direct solve (call before admmb_finalize; default off, or on with ADMMB_DETERMINISTIC=1 in the
  * environment).  By default the tile products of the triangular solves are accumulated with floating-point atomics, whose
  * order -- and therefore the last bits of x -- vary from run to run; with this option every tile stores its partial
- * sums and a second kernel per tree level adds them in a fixed order: two runs on the same input are bit-identical, like
- * the reference's serial solve, at about +40 % solve time (+12 % per ADMM iteration at 1 M tets).  The local step, the
+ * sums and the last tile to arrive at an output row adds them in a fixed order: two runs on the same input are
+ * bit-identical, like the reference's serial solve, at about +35 % solve time (+10 % per ADMM iteration at 1 M tets).  The local step, the
  * right-hand-side assembly and the explicit forces are deterministic in either mode. */
 int admmb_set_deterministic(admmb_ctx *ctx, int on);
 
