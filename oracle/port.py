@@ -73,7 +73,6 @@ class PortAdapter:
                 L.oracle_add_tets(self.h, int(b["kind"]), idx.shape[0], idx, float(b.get("p0", 0)), float(b.get("p1", 0)),
                                   float(b.get("p2", 0)), int(b.get("maxit", 10)))
             elif t == "tris":
-                assert int(b["kind"]) != 2, "FungTriangle is not restated in the port"
                 L.oracle_add_tris(self.h, int(b["kind"]), idx.shape[0], idx, float(b["stiffness"]), float(b.get("lmin", 0.0)),
                                   float(b.get("lmax", 9999999.0)), int(b.get("flag", 1)))
             elif t == "springs":

@@ -5,7 +5,7 @@
  * follows (A/ = /root/reference/deps/admm-elastic-sca).  It exists so that a checker is available where the
  * unmodified reference (oracle/_ref, built from /root/reference) is not; it is pinned against the reference's
  * golden dumps by tests/test_oracle_port.py: replayed from the reference's own inputs, the local step of every golden
- * iteration (z, u, optimiser state; all forces but FungTriangle, which is not restated here) is BIT-EXACT; free-running,
+ * iteration (z, u, optimiser state; every force class) is BIT-EXACT; free-running,
  * x agrees to rounding where the reference is reproducible and within its own sensitivity where it is not.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
  * leg may load it.  Nothing here is shared with the product's csrc/ (written separately on purpose).
  */
@@ -140,6 +140,16 @@ typedef struct { int model; double mu, lambda, k, s0[3]; } prob_t;
 
 static double obj_value(const prob_t *P, const double *x) {
 	double d0 = x[0] - P->s0[0], d1 = x[1] - P->s0[1], d2 = x[2] - P->s0[2];
+	if (P->model == 3) { /* FungProx::value TriangleForce.cpp:120-146 (b = 1); two unknowns, x[2] is an inert 0 */
+		double s3, I1, t1, t2, r0;
+		if (x[0] <= 0.0 || x[1] <= 0.0) return FLT_MAX_D;
+		s3 = 1.0 / (x[0] * x[1]);
+		I1 = x[0] * x[0] + x[1] * x[1] + s3 * s3;
+		t1 = P->mu / (1.0 * 2.0);
+		t2 = exp(1.0 * (I1 - 3.0)) - 1.0;
+		r0 = isfinite(t2) ? (t1 * t2) : FLT_MAX_D;
+		return r0 + (P->k * 0.5) * (d0 * d0 + d1 * d1);
+	}
 	if (x[0] < 0.0 || x[1] < 0.0 || x[2] < 0.0) return FLT_MAX_D;
 	if (P->model == 1) { /* NHProx::value :228-233 */
 		double det = x[0] * x[1] * x[2], I1 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2], l = log(det * det);
@@ -154,6 +164,18 @@ static double obj_value(const prob_t *P, const double *x) {
 }
 static void obj_grad(const prob_t *P, const double *x, double *g) {
 	int i;
+	if (P->model == 3) { /* FungProx::gradient TriangleForce.cpp:148-168 */
+		const double minval = 1.17549435082228751e-38; /* numeric_limits<float>::min() */
+		double sig3, I1, t1;
+		g[2] = 0.0;
+		if (fabs(x[0]) < minval || fabs(x[1]) < minval) { g[0] = g[1] = 1.0 * FLT_MAX_D; return; }
+		sig3 = 1.0 / (x[0] * x[1]);
+		I1 = (x[0] * x[0] + x[1] * x[1] + sig3 * sig3);
+		t1 = 0.5 * P->mu * exp(1.0 * (I1 - 3.0));
+		g[0] = t1 * (2.0 * x[0] - 2.0 / (x[0] * x[0] * x[0] * x[1] * x[1])) + P->k * (x[0] - P->s0[0]);
+		g[1] = t1 * (2.0 * x[1] - 2.0 / (x[1] * x[1] * x[1] * x[0] * x[0])) + P->k * (x[1] - P->s0[1]);
+		return;
+	}
 	if (P->model == 1) { /* NHProx::gradient :235-243 */
 		double det = x[0] * x[1] * x[2];
 		if (det <= 0.0) { g[0] = g[1] = g[2] = FLT_MAX_D; return; }
@@ -475,6 +497,12 @@ static void project_tri(force_t *f, const double *q, double *z) {
 			if (l0 > f->p2) { sc = f->p2 / f0; z[0] *= sc; z[1] *= sc; z[2] *= sc; }
 			if (l1 > f->p2) { sc = f->p2 / f1; z[3] *= sc; z[4] *= sc; z[5] *= sc; }
 		}
+	} else if (f->kind == 2) { /* FungTriangle::project TriangleForce.cpp:217-248: L-BFGS on the two singular values */
+		prob_t P;
+		double x2[3] = { S[0], S[1], 0.0 };
+		P.model = 3; P.mu = f->p0; P.lambda = 0.0; P.k = f->p0; P.s0[0] = S[0]; P.s0[1] = S[1]; P.s0[2] = 0.0;
+		f->last_iters = lbfgs(&P, x2, 10, 1e-6, &f->init_hess);
+		for (c = 0; c < 2; ++c) for (r = 0; r < 3; ++r) z[3 * c + r] = (U[r][0] * x2[0]) * V[c][0] + (U[r][1] * x2[1]) * V[c][1];
 	} else { /* TriArea::project :257-295 */
 		double S0[2] = { S[0], S[1] }, d[2] = { 0, 0 };
 		int i;
@@ -596,6 +624,7 @@ int oracle_add_tris(oracle_sys *S, int kind, int count, const int *idx, double s
 		area = fabs(det / 2.0);
 		f->w = (double)(sqrtf((float)stiffness) * sqrtf((float)area));
 		f->k = stiffness * area;
+		if (kind == 2) { f->w = sqrt(stiffness) * sqrt(area); f->k = stiffness; f->init_hess = 1.0; } /* FungTriangle::initialize :190-196 */
 	}
 	return 0;
 }

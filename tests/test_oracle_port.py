@@ -46,8 +46,6 @@ def test_known_answers_singletet_and_singlenode():
 @pytest.mark.parametrize("name", list(SCEN))
 def test_port_against_reference_golden(name):
     port = _port()
-    if name == "cloth_fung":
-        pytest.skip("FungTriangle (not reachable from ForceBuilder) is not restated in the C port; covered on the device")
     gold = np.load(os.path.join(GOLDEN, f"{name}.ref.npz"))
     scenario = dict(SCEN[name])
     scenario["scene"] = scenes.load_scene(os.path.join(GOLDEN, f"{name}.scene.npz"))
@@ -69,8 +67,6 @@ def test_port_local_step_is_bit_exact_teacher_forced(name):
     """The restatement is literal: replayed from the reference's own inputs (x entering the iteration, u and optimiser
     state of the previous one), every ADMM iteration's z, u and optimiser state come out bit for bit."""
     port = _port()
-    if name == "cloth_fung":
-        pytest.skip("FungTriangle is not restated in the C port")
     gold = np.load(os.path.join(GOLDEN, f"{name}.ref.npz"))
     scenario = dict(SCEN[name])
     scenario["scene"] = scenes.load_scene(os.path.join(GOLDEN, f"{name}.scene.npz"))
