@@ -8,4 +8,8 @@ namespace admmb {
 static const unsigned long long GLIBC_LOG_DATA[274] = {
 #include "glibc_log_data.inc"
 };
+// __exp_data of the same libm (tools/extract_glibc_exp.py): invln2N, shift, negln2hiN, negln2loN, C2..C5, tab[2*128]
+static const unsigned long long GLIBC_EXP_DATA[264] = {
+#include "glibc_exp_data.inc"
+};
 } // namespace admmb

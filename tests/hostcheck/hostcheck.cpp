@@ -52,5 +52,16 @@ void hc_svd3(const double *F, double *U, double *S, double *V, int oriented) {
 	if (oriented) oriented_svd3(F, U, S, V); else jacobi_svd3(F, U, S, V);
 }
 void hc_svd32(const double *F, double *Ut, double *S, double *V) { svd32(F, Ut, S, V); }
+// the libm clones against the libm of this box, element by element; returns the number of results that differ in any bit
+long hc_exp_mismatches(long n, const double *x) {
+	long bad = 0;
+	for (long i = 0; i < n; ++i) { const double a = glibc_exp(x[i]), b = exp(x[i]); if (memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) ++bad; }
+	return bad;
+}
+long hc_log_mismatches(long n, const double *x) {
+	long bad = 0;
+	for (long i = 0; i < n; ++i) { const double a = glibc_log(x[i]), b = log(x[i]); if (memcmp(&a, &b, 8) != 0 && !(a != a && b != b)) ++bad; }
+	return bad;
+}
 
 }

@@ -1,0 +1,42 @@
+"""The device cannot call the host libm, and CUDA's log / exp differ from glibc's in the last bit for a few percent of
+arguments -- enough to flip branches of the reference's truncated line search.  csrc/elastic_math.h therefore carries
+clones of glibc 2.39's `__log_fma` / `__exp_fma` (tables read from this image's libm.so.6 by tools/extract_glibc_*.py).
+Here the clones, compiled for the host by tests/hostcheck, are compared with the libm of this box bit for bit."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+HC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck", "libhostcheck.so")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def _lib():
+    if not os.path.exists(HC):
+        pytest.skip("tests/hostcheck not built (run __graft_entry__.build())")
+    L = C.CDLL(HC)
+    for f in (L.hc_exp_mismatches, L.hc_log_mismatches):
+        f.restype = C.c_long
+        f.argtypes = [C.c_long, _dp]
+    return L
+
+
+def test_exp_clone_matches_libm_bit_for_bit():
+    L = _lib()
+    rng = np.random.default_rng(1)
+    sets = [rng.uniform(-20, 20, 2_000_000), rng.uniform(-1, 1, 1_000_000), rng.uniform(-1e-10, 1e-10, 200_000),
+            rng.uniform(600, 720, 300_000), rng.uniform(-760, -600, 300_000), rng.uniform(-1100, 1100, 300_000),
+            np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 709.782712893384, 709.8, -745.2, -745.13321910194122, -708.4, 1e-300,
+                      -1e-300, 5e-324, 1024.0, -1075.0, 2.0 ** -54, 2.0 ** -55])]
+    for x in sets:
+        assert L.hc_exp_mismatches(len(x), np.ascontiguousarray(x)) == 0
+
+
+def test_log_clone_matches_libm_bit_for_bit():
+    L = _lib()
+    rng = np.random.default_rng(2)
+    sets = [np.exp(rng.uniform(-30, 30, 2_000_000)), rng.uniform(0.9, 1.1, 1_000_000), rng.uniform(1e-310, 1e-300, 100_000),
+            np.array([0.0, -0.0, 1.0, np.inf, -1.0, np.nan, 5e-324, 1.7976931348623157e308])]
+    for x in sets:
+        assert L.hc_log_mismatches(len(x), np.ascontiguousarray(x)) == 0

@@ -103,15 +103,9 @@ def test_iteration_teacher_forced(name):
     assert worst_local <= TOL_ITER
     assert worst_x <= TOL_ITER
     # Bit-exactness: tets (ARAP, volume, StVK, and NeoHookean through the glibc log clone), triangles (through the
-    # restated Eigen 3x2 JacobiSVD: column-pivoting Householder QR + 2x2 Jacobi), springs, hinges, anchors and
-    # collisions restate the reference's arithmetic literally.
-    has_fung = any(b["type"] == "tris" and int(b["kind"]) == 2 for b in scenario["scene"]["batches"])
-    if has_fung:
-        # FungTriangle: exp() of the device libm differs from glibc's in the last bit and the truncated L-BFGS
-        # amplifies it (measured 7e-12); the 1e-9 gate above applies
-        pass
-    else:
-        assert n_exact == n_total, f"{name}: {n_total - n_exact} of {n_total} local-step vectors differ in the last bits"
+    # restated Eigen 3x2 JacobiSVD: column-pivoting Householder QR + 2x2 Jacobi; FungTriangle through the glibc exp clone),
+    # springs, hinges, anchors and collisions restate the reference's arithmetic literally.
+    assert n_exact == n_total, f"{name}: {n_total - n_exact} of {n_total} local-step vectors differ in the last bits"
 
 
 @pytest.mark.parametrize("N,kind,label,frames", [(16, scenes.TET_NH, "nh", 4), (12, scenes.TET_STVK, "stvk", 3), (14, scenes.TET_ARAP, "arap", 2)])
