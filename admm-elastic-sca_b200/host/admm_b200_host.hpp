@@ -348,7 +348,8 @@ public:
 		int device;      // (new) CUDA device of this system
 		int solver;      // (new) ADMMB_SOLVER_DIRECT / ADMMB_SOLVER_PCG
 		bool pin_host;   // (new) page-lock the storage of m_x / m_v so step() transfers it by direct DMA
-		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT), pin_host(true) {}
+		bool deterministic; // (new) atomic-free solve: runs are bit-reproducible, like the reference's serial solve (about 10 % slower)
+		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT), pin_host(true), deterministic(false) {}
 	} settings;
 
 	double elapsed_s;
@@ -414,6 +415,7 @@ inline bool System::initialize() {
 	const int n = (int)(m_x.size() / 3);
 	if (admmb_set_nodes(ctx, n, m_x.data(), m_masses.data()) < 0) return fail("set_nodes");
 	admmb_set_solver(ctx, settings.solver, 0.0, 0);
+	if (settings.deterministic) admmb_set_deterministic(ctx, 1);
 
 	// flatten maximal runs of forces that share class and material into batches, keeping the force order
 	batches.clear();
