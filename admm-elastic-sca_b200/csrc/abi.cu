@@ -52,7 +52,7 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 	for (Batch &b : ctx->batches) free_batch(b);
 	for (ExplicitEntry &e : ctx->explicit_forces) { e.d_idx.free(); e.d_level_ptr.free(); }
 	ctx->d_x.free(); ctx->d_v.free(); ctx->d_xbar.free(); ctx->d_Mxbar.free(); ctx->d_currx.free(); ctx->d_b.free(); ctx->d_m.free();
-	ctx->d_io.free(); ctx->d_node_perm.free(); ctx->d_P.free(); ctx->d_vert_ptr.free(); ctx->d_vert_slots.free();
+	ctx->d_bad.free(); ctx->d_io.free(); ctx->d_node_perm.free(); ctx->d_P.free(); ctx->d_vert_ptr.free(); ctx->d_vert_slots.free();
 	drop_iteration_graph(ctx);
 	pcg_destroy(ctx);
 	direct_destroy(ctx);
@@ -220,6 +220,23 @@ extern "C" int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *i
 extern "C" int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3) {
 	if (!ctx) return ADMMB_E_ARG;
 	return add_explicit(ctx, 2, ntris, tris3, 3, dir3, "wind");
+}
+
+extern "C" int admmb_set_check_finite(admmb_ctx *ctx, int on) {
+	CHECK_CTX(ctx);
+	ctx->check_finite = on != 0;
+	return ADMMB_OK;
+}
+
+// after a synchronisation point: has any frame since the last check produced a non-finite position?
+static int check_finite(admmb_ctx *ctx) {
+	if (!ctx->check_finite) return ADMMB_OK;
+	int bad = 0;
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (!bad) return ADMMB_OK;
+	ADMMB_CUDA(ctx, ctx->d_bad.zero(ctx->stream));
+	ADMMB_FAIL(ctx, ADMMB_E_NUMERIC, "positions are not finite after the step (diverged, or NaN / Inf in the inputs)");
 }
 
 extern "C" int admmb_set_deterministic(admmb_ctx *ctx, int on) {
@@ -407,6 +424,8 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		ADMMB_CUDA(ctx, ctx->d_Mxbar.alloc(3 * npad));
 		ADMMB_CUDA(ctx, ctx->d_currx.upload(xi, s));
 		ADMMB_CUDA(ctx, ctx->d_b.alloc(3 * npad));
+		ADMMB_CUDA(ctx, ctx->d_bad.alloc(1));
+		ADMMB_CUDA(ctx, ctx->d_bad.zero(s));
 		ADMMB_CUDA(ctx, ctx->d_io.alloc(6 * (size_t)n));
 		ADMMB_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, 6 * (size_t)n * sizeof(double)));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -670,8 +689,8 @@ extern "C" int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, dou
 	ctx->elapsed_s += ctx->dt;
 	rc = admmb_download_xv(ctx, x3n_inout, v3n_inout);
 	if (rc) return rc;
-	if (timed) { e1 = next_event(ctx); return collect_timing(ctx, admm_iters, e0, e1); }
-	return ADMMB_OK;
+	if (timed) { e1 = next_event(ctx); if ((rc = collect_timing(ctx, admm_iters, e0, e1))) return rc; }
+	return check_finite(ctx);
 }
 
 extern "C" int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout, double *x_it, double *z_it,
@@ -748,7 +767,7 @@ extern "C" int admmb_sync(admmb_ctx *ctx) {
 		if (cudaEventElapsedTime(&ms, ctx->ev_region[0], ctx->ev_region[1]) == cudaSuccess) ctx->last_region_ms = ms;
 		else cudaGetLastError();
 	}
-	return ADMMB_OK;
+	return check_finite(ctx);
 }
 
 extern "C" int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames) {

@@ -156,6 +156,8 @@ struct admmb_ctx {
 	int dist_rank = 0, dist_world = 1;
 	int own0 = 0, own1 = 0, chunk = 0;  // chunk = ceil(n / world); node vectors are allocated world * chunk long
 	void *nccl_comm = nullptr;
+	bool check_finite = false;  // admmb_set_check_finite: steps fail with ADMMB_E_NUMERIC once x is not finite
+	admmb::DevBuf<int> d_bad;   // set by k_frame_end when a position is not finite
 	bool deterministic = false; // admmb_set_deterministic: atomic-free (bit-reproducible) direct solve
 	bool use_graph = true;
 	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)

@@ -75,12 +75,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_frame_begin(int n3, double dt, 
 }
 
 __global__ void __launch_bounds__(VEC_THREADS) k_frame_end(int n3, double inv_dt, double *__restrict__ x, double *__restrict__ v,
-                                                           const double *__restrict__ currx) {
+                                                           const double *__restrict__ currx, int *__restrict__ bad) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n3) return;
 	const double cx = currx[t];
 	v[t] = (cx - x[t]) * inv_dt;
 	x[t] = cx;
+	if (!isfinite(cx)) *bad = 1; // failure detection (admmb_set_check_finite): every writer stores the same value
 }
 
 int launch_frame_begin(admmb_ctx *ctx) {
@@ -111,7 +112,7 @@ int launch_frame_begin(admmb_ctx *ctx) {
 
 int launch_frame_end(admmb_ctx *ctx) {
 	const int n3 = 3 * ctx->n;
-	k_frame_end<<<(n3 + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n3, 1.0 / ctx->dt, ctx->d_x.p, ctx->d_v.p, ctx->d_currx.p);
+	k_frame_end<<<(n3 + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n3, 1.0 / ctx->dt, ctx->d_x.p, ctx->d_v.p, ctx->d_currx.p, ctx->d_bad.p);
 	ctx->launches++;
 	ADMMB_CUDA(ctx, cudaGetLastError());
 	return ADMMB_OK;

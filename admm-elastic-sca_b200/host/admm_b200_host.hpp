@@ -349,7 +349,8 @@ public:
 		int solver;      // (new) ADMMB_SOLVER_DIRECT / ADMMB_SOLVER_PCG
 		bool pin_host;   // (new) page-lock the storage of m_x / m_v so step() transfers it by direct DMA
 		bool deterministic; // (new) atomic-free solve: runs are bit-reproducible, like the reference's serial solve (about 10 % slower)
-		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT), pin_host(true), deterministic(false) {}
+		bool check_finite;  // (new) step() returns false once positions are not finite (the reference's step() always returns true)
+		Settings() : timestep_s(0.04), verbose(1), admm_iters(10), device(0), solver(ADMMB_SOLVER_DIRECT), pin_host(true), deterministic(false), check_finite(false) {}
 	} settings;
 
 	double elapsed_s;
@@ -416,6 +417,7 @@ inline bool System::initialize() {
 	if (admmb_set_nodes(ctx, n, m_x.data(), m_masses.data()) < 0) return fail("set_nodes");
 	admmb_set_solver(ctx, settings.solver, 0.0, 0);
 	if (settings.deterministic) admmb_set_deterministic(ctx, 1);
+	if (settings.check_finite) admmb_set_check_finite(ctx, 1);
 
 	// flatten maximal runs of forces that share class and material into batches, keeping the force order
 	batches.clear();

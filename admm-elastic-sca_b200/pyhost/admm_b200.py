@@ -27,7 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
-    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic", "admmb_set_check_finite",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
     L.admmb_set_gravity.argtypes = [vp, C.c_int, _dp]
     L.admmb_set_host_threads.argtypes = [C.c_int]
     L.admmb_set_deterministic.argtypes = [vp, C.c_int]
+    L.admmb_set_check_finite.argtypes = [vp, C.c_int]
     L.admmb_register_host_buffer.argtypes = [vp, vp, C.c_long]
     L.admmb_download_x_f32.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]
     L.admmb_unregister_host_buffer.argtypes = [vp, vp]

@@ -102,6 +102,10 @@ int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *di
  * packing); n <= 0 restores the OpenMP default.  Several ranks on one node should share the cores: cores / ranks each. */
 int admmb_set_host_threads(int n);
 
+/* Failure detection (default off: System::step() of the reference always returns true, System.cpp:74): when on,
+ * admmb_step / admmb_sync return ADMMB_E_NUMERIC once a frame has produced a position that is not finite. */
+int admmb_set_check_finite(admmb_ctx *ctx, int on);
+
 /* Bit-reproducible direct solve (call before admmb_finalize; default off, or on with ADMMB_DETERMINISTIC=1 in the
  * environment).  By default the tile products of the triangular solves are accumulated with floating-point atomics, whose
  * order -- and therefore the last bits of x -- vary from run to run; with this option every tile stores its partial

@@ -171,3 +171,24 @@ def test_deterministic_solve_is_bit_reproducible_and_agrees_with_the_default():
     arap = scenes.cube_scene(8, kind=scenes.TET_ARAP, seed=3)
     c, d = run(arap, True), run(arap, False)
     assert np.abs(c - d).max() <= 1e-12 * np.abs(c).max()
+
+
+def test_check_finite_reports_divergence():
+    """admmb_set_check_finite: once a frame produces a non-finite position the step fails with ADMMB_E_NUMERIC (the
+    reference's step() always returns true, System.cpp:74, so this is off by default)."""
+    sc = scenes.cloth_scene(6, 5, springs=False, wind=(3.0, 1.0, 4.0), iters=6, name="diverge")
+    a = admm_b200.System(sc, iters=0)      # explicit wind drag without the implicit solve is unstable: NaN within ~10 frames
+    assert a.L.admmb_set_check_finite(a.h, 1) == 0
+    failed_at = None
+    for f in range(40):
+        rc = a.L.admmb_step(a.h, 0, a.m_x, a.m_v)
+        if rc != 0:
+            failed_at = f
+            assert rc == -4 and b"not finite" in a.L.admmb_last_error(a.h)
+            break
+    assert failed_at is not None and not np.isfinite(a.m_x).all()
+    a.close()
+    b = admm_b200.System(sc, iters=0)      # default: no check, the call keeps returning 0 like the reference
+    for f in range(failed_at + 1):
+        assert b.L.admmb_step(b.h, 0, b.m_x, b.m_v) == 0
+    b.close()
