@@ -639,24 +639,39 @@ extern "C" int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *
 	return ADMMB_OK;
 }
 
-extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
-	CHECK_READY(ctx);
+// download of x / v in two halves: enqueue (permute + device-to-host copy on the stream) and, after the stream has been
+// synchronised, finish (copy out of the staging area for destinations that are not page-locked)
+static int enqueue_download(admmb_ctx *ctx, double *x3n, double *v3n) {
 	const size_t n3 = 3 * (size_t)ctx->n;
 	cudaStream_t s = ctx->stream;
 	double *out[2] = { x3n, v3n };
 	const double *src[2] = { ctx->d_x.p, ctx->d_v.p };
-	bool staged[2] = { false, false };
 	for (int k = 0; k < 2; ++k) {
+		ctx->pending_out[k] = out[k];
 		if (!out[k]) continue;
 		int rc = launch_permute_out(ctx, src[k], ctx->d_io.p + k * n3);
 		if (rc) return rc;
-		staged[k] = !is_registered(ctx, out[k], n3 * sizeof(double));
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(staged[k] ? ctx->h_pin + k * n3 : out[k], ctx->d_io.p + k * n3, n3 * sizeof(double),
+		ctx->pending_staged[k] = !is_registered(ctx, out[k], n3 * sizeof(double));
+		ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->pending_staged[k] ? ctx->h_pin + k * n3 : out[k], ctx->d_io.p + k * n3, n3 * sizeof(double),
 		                                cudaMemcpyDeviceToHost, s));
 	}
-	ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
-	for (int k = 0; k < 2; ++k)
-		if (out[k] && staged[k]) staged_copy(out[k], ctx->h_pin + k * n3, n3 * sizeof(double));
+	return ADMMB_OK;
+}
+static void finish_download(admmb_ctx *ctx) {
+	const size_t n3 = 3 * (size_t)ctx->n;
+	for (int k = 0; k < 2; ++k) {
+		if (ctx->pending_out[k] && ctx->pending_staged[k]) staged_copy(ctx->pending_out[k], ctx->h_pin + k * n3, n3 * sizeof(double));
+		ctx->pending_out[k] = nullptr;
+		ctx->pending_staged[k] = false;
+	}
+}
+
+extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
+	CHECK_READY(ctx);
+	int rc = enqueue_download(ctx, x3n, v3n);
+	if (rc) return rc;
+	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	finish_download(ctx);
 	return ADMMB_OK;
 }
 
@@ -691,6 +706,19 @@ extern "C" int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, dou
 	if (rc) return rc;
 	if (timed) { e1 = next_event(ctx); if ((rc = collect_timing(ctx, admm_iters, e0, e1))) return rc; }
 	return check_finite(ctx);
+}
+
+extern "C" int admmb_step_async(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout) {
+	CHECK_READY(ctx);
+	if (admm_iters < 0 || !x3n_inout || !v3n_inout) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step_async: bad arguments");
+	if (ctx->pending_out[0] || ctx->pending_out[1]) ADMMB_FAIL(ctx, ADMMB_E_STATE, "step_async: the previous asynchronous step has not been collected with admmb_sync");
+	int rc = admmb_upload_xv(ctx, x3n_inout, v3n_inout);
+	if (rc) return rc;
+	if ((rc = launch_frame_begin(ctx))) return rc;
+	if ((rc = run_iterations(ctx, admm_iters))) return rc;
+	if ((rc = launch_frame_end(ctx))) return rc;
+	ctx->elapsed_s += ctx->dt;
+	return enqueue_download(ctx, x3n_inout, v3n_inout);
 }
 
 extern "C" int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout, double *x_it, double *z_it,
@@ -762,6 +790,7 @@ extern "C" int admmb_step_resident_async(admmb_ctx *ctx, int admm_iters, int fra
 extern "C" int admmb_sync(admmb_ctx *ctx) {
 	CHECK_READY(ctx);
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	finish_download(ctx);
 	if (ctx->ev_region[0]) {
 		float ms = 0.f;
 		if (cudaEventElapsedTime(&ms, ctx->ev_region[0], ctx->ev_region[1]) == cudaSuccess) ctx->last_region_ms = ms;

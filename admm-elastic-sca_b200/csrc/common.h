@@ -138,6 +138,8 @@ struct admmb_ctx {
 
 	// pinned host staging
 	double *h_pin = nullptr;
+	double *pending_out[2] = { nullptr, nullptr }; // admmb_step_async: host destinations of the enqueued x / v download
+	bool pending_staged[2] = { false, false };
 	std::vector<std::pair<char *, size_t>> host_regs; // caller buffers page-locked by admmb_register_host_buffer
 
 	// scalar system matrix (host CSR, internal order, full symmetric pattern)

@@ -27,7 +27,7 @@ EXPORTS = [
     "admmb_get_anchor_targets", "admmb_set_batch_weights", "admmb_get_batch_weights", "admmb_recompute_weights",
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
-    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic", "admmb_set_check_finite",
+    "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic", "admmb_set_check_finite", "admmb_step_async",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
     L.admmb_step_resident.argtypes = [vp, C.c_int, C.c_int]
     L.admmb_step_resident_async.argtypes = [vp, C.c_int, C.c_int]
     L.admmb_sync.argtypes = [vp]
+    L.admmb_step_async.argtypes = [vp, C.c_int, _dp, _dp]
     L.admmb_upload_xv.argtypes = [vp, vp, vp]
     L.admmb_download_xv.argtypes = [vp, vp, vp]
     L.admmb_update_anchor_targets.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -259,6 +260,10 @@ class System:
     def step_resident_async(self, frames=1, iters=None):
         """Enqueue only (scene ensembles: several Systems in flight on one GPU); pair with sync()."""
         self._ck(self.L.admmb_step_resident_async(self.h, int(self.admm_iters if iters is None else iters), int(frames)))
+
+    def step_async(self, iters=None):
+        """System::step() enqueued only: m_x / m_v are read now and written when sync() returns."""
+        self._ck(self.L.admmb_step_async(self.h, int(self.admm_iters if iters is None else iters), self.m_x, self.m_v))
 
     def sync(self):
         self._ck(self.L.admmb_sync(self.h))

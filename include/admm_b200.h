@@ -156,6 +156,10 @@ int admmb_step_resident(admmb_ctx *ctx, int admm_iters, int frames);
  * waits for the context's stream and fills admmb_last_region_ms. */
 int admmb_step_resident_async(admmb_ctx *ctx, int admm_iters, int frames);
 int admmb_sync(admmb_ctx *ctx);
+/* admmb_step without the final wait: host x / v are read at the call (staged at once unless page-locked), the step is
+ * enqueued, and x / v are written when admmb_sync returns -- the buffers must stay valid and untouched until then.  With
+ * page-locked buffers (admmb_register_host_buffer) several contexts overlap their transfers and their compute. */
+int admmb_step_async(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout);
 int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n);   /* either may be NULL */
 int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n);             /* either may be NULL */
 

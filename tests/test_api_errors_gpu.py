@@ -192,3 +192,33 @@ def test_check_finite_reports_divergence():
     for f in range(failed_at + 1):
         assert b.L.admmb_step(b.h, 0, b.m_x, b.m_v) == 0
     b.close()
+
+
+def test_step_async_with_host_buffers_matches_step():
+    """admmb_step_async + admmb_sync = admmb_step, for page-locked and for plain host buffers, several scenes in flight."""
+    scs = [scenes.cube_scene(3, kind=scenes.TET_ARAP, iters=6, seed=20 + i) for i in range(3)]
+    ref = []
+    for sc in scs:
+        s = admm_b200.System(sc)
+        s.set_x(sc["x_after_init"])
+        for _ in range(3):
+            s.step()
+        ref.append((s.m_x.copy(), s.m_v.copy()))
+        s.close()
+    for pin in (True, False):
+        sims = [admm_b200.System(sc, pin_host=pin) for sc in scs]
+        for s, sc in zip(sims, scs):
+            s.set_x(sc["x_after_init"])
+        for _ in range(3):
+            for s in sims:
+                s.step_async()
+            for s in sims:
+                s.sync()
+        for s, (x, v) in zip(sims, ref):
+            assert np.abs(s.m_x - x).max() <= 1e-12 and np.abs(s.m_v - v).max() <= 1e-10
+        # a second step_async before sync is a state error
+        assert sims[0].L.admmb_step_async(sims[0].h, 6, sims[0].m_x, sims[0].m_v) == 0
+        assert sims[0].L.admmb_step_async(sims[0].h, 6, sims[0].m_x, sims[0].m_v) == -2
+        sims[0].sync()
+        for s in sims:
+            s.close()
