@@ -21,9 +21,13 @@ XML = dict(bunnyexpand="bunnyexpand.xml", windyflag="cloth.xml", poordillo="poor
 @pytest.mark.parametrize("name", list(XML))
 def test_reference_scene_layer_runs_on_the_gpu_solver(name, tmp_path):
     runner = os.path.join(DROPIN, "ref_scene_runner")
-    xml = os.path.join(DROPIN, "scenes", name, XML[name])
-    if not (os.path.exists(runner) and os.path.exists(xml)):
+    archive = os.path.join(DROPIN, "scenes.tar")
+    if not (os.path.exists(runner) and os.path.exists(archive)):
         pytest.skip("tests/dropin not built (needs the reference tree at build time: __graft_entry__.build())")
+    import tarfile
+    with tarfile.open(archive) as tf:
+        tf.extractall(tmp_path, members=[m for m in tf.getmembers() if m.name.startswith(name + "/")], filter="data")
+    xml = str(tmp_path / name / XML[name])
     gold = np.load(os.path.join(GOLDEN, f"shipped_{name}.ref.npz"))
     frames = SHIPPED_FRAMES[name]
     out = str(tmp_path / "x.bin")
