@@ -40,3 +40,17 @@ def test_log_clone_matches_libm_bit_for_bit():
             np.array([0.0, -0.0, 1.0, np.inf, -1.0, np.nan, 5e-324, 1.7976931348623157e308])]
     for x in sets:
         assert L.hc_log_mismatches(len(x), np.ascontiguousarray(x)) == 0
+
+
+@pytest.mark.parametrize("tool,inc", [("extract_glibc_exp.py", "glibc_exp_data.inc")])
+def test_committed_table_is_what_this_libm_holds(tool, inc):
+    """Provenance of the constants: the committed table equals what tools/extract_glibc_exp.py reads from the libm of this
+    box (skipped if libm moved its tables, in which case the sweep tests above are the authority)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", tool)], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("libm layout differs from glibc 2.39-0ubuntu8.5: " + r.stderr.strip().splitlines()[-1])
+    committed = open(os.path.join(root, "admm-elastic-sca_b200", "csrc", inc)).read()
+    assert r.stdout.split() == committed.split()
