@@ -184,15 +184,21 @@ LIVE = {
 }
 
 
+LIVE_SENS_SEEDS = (99, 100, 101, 102)
+
+
 def _ref_pair(scenario, dump):
-    """Reference run and the reference's own sensitivity (second run from positions perturbed by 1e-15)."""
+    """Reference run and the reference's own sensitivity: the worst deviation of runs from positions perturbed by 1e-15
+    with a few different sign patterns (the response is heavy-tailed, one pattern can under-state it)."""
     ra = RefAdapter(scenario["scene"])
     gold = run_scenario(ra, scenario, dump=dump)
     ra.close()
-    ra = RefAdapter(scenario["scene"])
-    per = run_scenario(ra, scenario, dump=dump, perturb=1e-15)
-    ra.close()
-    return gold, per
+    pers = []
+    for seed in LIVE_SENS_SEEDS:
+        ra = RefAdapter(scenario["scene"])
+        pers.append(run_scenario(ra, scenario, dump=dump, perturb=1e-15, seed=seed))
+        ra.close()
+    return gold, pers
 
 
 @pytest.mark.parametrize("name", list(LIVE))
@@ -206,7 +212,7 @@ def test_live_reference_per_iteration(name):
     ad.close()
     report, ok = [], True
     for key in ("x_it", "z_it", "u_it", "x", "v"):
-        err, sens = _worst(res[key], gold[key]), _worst(per[key], gold[key])
+        err, sens = _worst(res[key], gold[key]), max(_worst(p[key], gold[key]) for p in per)
         tol = max(TOL_ITER, SENS_FACTOR * sens)
         report.append(f"{key} {err:.1e} (ref self-sens {sens:.1e})")
         ok = ok and err <= tol
@@ -226,6 +232,6 @@ def test_trajectory_100_frames(kind, label):
     res = run_scenario(ad, scenario, dump=False)
     ad.close()
     err = max(rel_l2(res["x"][f], gold["x"][f]) for f in range(100))
-    sens = max(rel_l2(per["x"][f], gold["x"][f]) for f in range(100))
+    sens = max(rel_l2(p["x"][f], gold["x"][f]) for p in per for f in range(100))
     print(f"trajectory/{label}: max rel-L2 over 100 frames = {err:.2e} (reference self-sensitivity {sens:.2e})")
     assert err <= max(TOL_TRAJ, SENS_FACTOR * sens)
