@@ -36,6 +36,13 @@ def test_reference_singletet_sample_runs_on_the_gpu_solver():
     assert m.group(1) == "171.571"   # A/samples/singletet.cpp:49 prints with default precision
 
 
+def test_plain_c_example_of_the_abi():
+    """examples/abi_minimal.c (C99, -pedantic -Werror): the singletet scene straight through the C ABI."""
+    out = subprocess.run([_need("abi_minimal")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "Node 4 x: 171.571"
+
+
 def test_reference_singlenode_sample_runs_on_the_gpu_solver():
     out = subprocess.run([_need("ref_singlenode")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
