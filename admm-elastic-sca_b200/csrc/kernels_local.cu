@@ -76,6 +76,7 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 	a.x = d_x;
 	a.P = ctx->d_P.p + 3 * (size_t)b.slot_base;
 	a.p0 = b.p0; a.p1 = b.p1; a.p2 = b.p2; a.max_iterations = b.max_iterations; a.flag = b.flag;
+	a.kprox = std::min(b.p0, b.p1);
 	a.shape_kind = b.d_shape_kind.p; a.shape_params = b.d_shape_params.p; a.nshapes = (int)b.shape_kind.size();
 	const int grid = (b.nlocal + LOCAL_THREADS - 1) / LOCAL_THREADS;
 	cudaStream_t s = ctx->stream;

@@ -22,6 +22,7 @@ struct LocalArgs {
 	const double *x;      // [n][3]
 	double *P;            // [slots][3], already offset to this batch's first slot
 	double p0, p1, p2;
+	double kprox;         // hyperelastic tets: the prox penalty k = min(mu, lambda), the same for every tet (TetForce.cpp:306)
 	int max_iterations, flag;
 	const int *shape_kind;
 	const double *shape_params;
@@ -92,7 +93,7 @@ template <class Model, int MH>
 ADMMB_HD void local_tet_hyper(const LocalArgs &a, const int e, double *park, const int ps) {
 	const int n = a.count;
 	ProxParams P;
-	P.mu = a.p0; P.lambda = a.p1; P.k = a.kk[e];
+	P.mu = a.p0; P.lambda = a.p1; P.k = a.kprox;
 	{
 		double B[12], q[9], U[9], V[9];
 		tet_load_Dx(a, e, B, q);

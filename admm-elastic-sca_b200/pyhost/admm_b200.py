@@ -28,6 +28,7 @@ EXPORTS = [
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
     "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic", "admmb_set_check_finite", "admmb_step_async",
+    "admmb_probe_fp64", "admmb_debug_fastmath_selftest",
 ]
 
 
@@ -98,8 +99,30 @@ def lib():
     L.admmb_last_region_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.admmb_dist_unique_id.argtypes = [C.c_char_p]
     L.admmb_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.admmb_probe_fp64.argtypes = [C.c_int, _dp]
+    L.admmb_debug_fastmath_selftest.argtypes = [C.c_int, C.c_ulonglong, C.c_long, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")]
     _lib = L
     return L
+
+
+def probe_fp64(device=0):
+    """Measured FP64 issue rates on `device`: dict with DFMA / DADD / DMUL 1e12 thread-instructions/s, the dependent-DFMA
+    latency in cycles, SM count and max SM clock (admmb_probe_fp64)."""
+    out = np.zeros(6)
+    rc = lib().admmb_probe_fp64(int(device), out)
+    if rc != 0:
+        raise RuntimeError(f"admmb_probe_fp64 failed ({rc})")
+    return {"dfma_tinst_s": out[0], "dadd_tinst_s": out[1], "dmul_tinst_s": out[2], "dfma_dependent_cycles": out[3],
+            "sms": int(out[4]), "sm_max_mhz": out[5]}
+
+
+def fastmath_selftest(samples=1 << 26, seed=1, device=0):
+    """(mismatches[4], fallbacks[4]) of the exact fast division / reciprocal / sqrt paths against the operators."""
+    out = np.zeros(8, dtype=np.uint64)
+    rc = lib().admmb_debug_fastmath_selftest(int(device), int(seed), int(samples), out)
+    if rc != 0:
+        raise RuntimeError(f"admmb_debug_fastmath_selftest failed ({rc})")
+    return out[:4].astype(np.int64), out[4:].astype(np.int64)
 
 
 def _i32(a):

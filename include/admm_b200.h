@@ -221,6 +221,19 @@ int admmb_timing_read(admmb_ctx *ctx, double *ms4, long *iters, int reset);
 /* Device time (CUDA events on the context's stream) of the whole last admmb_step_resident call, all frames. */
 int admmb_last_region_ms(admmb_ctx *ctx, double *ms);
 
+/* ---- probes (no context) ----------------------------------------------------------------------- */
+/* FP64 denominators of the local step's roofline, measured on `device` (SURVEY 8d asks for a measured FP64 peak):
+ * out6[0..2] = 1e12 thread-instructions/s of independent DFMA / DADD / DMUL chains (flop/s = 2x for DFMA);
+ * out6[3] = SM cycles per DFMA of ONE dependent chain (the latency a warp without instruction-level parallelism pays);
+ * out6[4] = number of SMs; out6[5] = maximum SM clock in MHz.  The local step is compiled without multiply-add
+ * contraction (the reference's x86 arithmetic rounds twice), so its attainable rate is the DADD / DMUL one. */
+int admmb_probe_fp64(int device, double *out6);
+/* Self-test of the exact fast paths for division / reciprocal / square root used by the local step (csrc/elastic_math.h)
+ * against the plain operators on `samples` pseudo-random operand sets of every class (any bit pattern, moderate,
+ * near 1, extreme exponents, zeros and powers of two).  counts8[0..3] = results that differ in any bit from a / y, three
+ * quotients sharing one reciprocal, 1 / x, sqrt(x) (must all be 0); counts8[4..7] = how often each took its fallback. */
+int admmb_debug_fastmath_selftest(int device, unsigned long long seed, long samples, unsigned long long *counts8);
+
 #ifdef __cplusplus
 }
 #endif

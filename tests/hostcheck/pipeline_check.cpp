@@ -60,7 +60,7 @@ extern "C" int hc_batch_local(int type, int kind, int n, const double *x_rest, i
 	a.count = count; a.idx = idx_soa.data(); a.S = S.data(); a.w = b.w.data(); a.wdt2 = wdt2.data(); a.kk = b.kk.data();
 	a.aux = aux.data(); a.u = u.data(); a.z = z.data(); a.state = st.data(); a.its = its.data();
 	a.active = (type == BT_MOVING_ANCHORS) ? b.active.data() : nullptr;
-	a.x = x_cur; a.P = P.data(); a.p0 = p0; a.p1 = p1; a.p2 = p2; a.max_iterations = maxit; a.flag = flag;
+	a.x = x_cur; a.P = P.data(); a.p0 = p0; a.p1 = p1; a.p2 = p2; a.kprox = std::min(p0, p1); a.max_iterations = maxit; a.flag = flag;
 	a.shape_kind = b.shape_kind.data(); a.shape_params = b.shape_params.data(); a.nshapes = nshapes;
 	for (int e = 0; e < count; ++e) {
 		switch (type) {
