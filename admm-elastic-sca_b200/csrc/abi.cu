@@ -68,7 +68,12 @@ extern "C" int admmb_destroy(admmb_ctx *ctx) {
 
 #define CHECK_CTX(ctx) do { if (!(ctx)) return ADMMB_E_ARG; cudaSetDevice((ctx)->device); } while (0)
 #define CHECK_BUILDING(ctx) do { CHECK_CTX(ctx); if ((ctx)->finalized) ADMMB_FAIL(ctx, ADMMB_E_STATE, "system already finalized"); } while (0)
-#define CHECK_READY(ctx) do { CHECK_CTX(ctx); if (!(ctx)->finalized) ADMMB_FAIL(ctx, ADMMB_E_STATE, "admmb_finalize has not been called"); } while (0)
+#define CHECK_READY(ctx) do { CHECK_CTX(ctx); if (!(ctx)->finalized) ADMMB_FAIL(ctx, ADMMB_E_STATE, "admmb_finalize has not been called"); \
+	if ((ctx)->broken) ADMMB_FAIL(ctx, ADMMB_E_STATE, "the context is unusable: admmb_recompute_weights failed, the factor no longer matches the weights (call admmb_recompute_weights again with valid weights)"); } while (0)
+// Between admmb_step_async and admmb_sync the context's staging areas (pinned host block, device I/O block) and the
+// pending-download record hold the step's results: every entry point that would overwrite them refuses to run.
+#define CHECK_NO_PENDING(ctx, what) do { if ((ctx)->pending_out[0] || (ctx)->pending_out[1]) \
+	ADMMB_FAIL(ctx, ADMMB_E_STATE, what ": an asynchronous step is pending, collect it with admmb_sync first"); } while (0)
 
 extern "C" int admmb_set_nodes(admmb_ctx *ctx, int n, const double *x3n, const double *m3n) {
 	CHECK_BUILDING(ctx);
@@ -209,6 +214,13 @@ extern "C" int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3) {
 	if ((size_t)id >= ctx->explicit_forces.size()) ADMMB_FAIL(ctx, ADMMB_E_ARG, "unknown explicit force id %d", id);
 	for (int j = 0; j < 3; ++j) ctx->explicit_forces[id].dir[j] = dir3[j];
 	return id;
+}
+
+extern "C" int admmb_enable_explicit(admmb_ctx *ctx, int id, int on) {
+	CHECK_CTX(ctx);
+	if (id < 0 || (size_t)id >= ctx->explicit_forces.size()) ADMMB_FAIL(ctx, ADMMB_E_ARG, "unknown explicit force id %d", id);
+	ctx->explicit_forces[id].enabled = on != 0;
+	return ADMMB_OK;
 }
 
 extern "C" int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *idx, const double *dir3) {
@@ -354,8 +366,8 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 	ctx->chunk = (n + ctx->dist_world - 1) / ctx->dist_world;
 	ctx->own0 = std::min(n, ctx->dist_rank * ctx->chunk);
 	ctx->own1 = std::min(n, ctx->own0 + ctx->chunk);
-	if (ctx->dist_world > 1 && ctx->solver != ADMMB_SOLVER_PCG)
-		ADMMB_FAIL(ctx, ADMMB_E_STATE, "a mesh partitioned over ranks needs ADMMB_SOLVER_PCG (sparse triangular solves do not shard: replicas only)");
+	// (both solvers run on a partitioned mesh: PCG partitions its rows; the direct solve does not shard -- sparse triangular
+	// solves are a dependency chain -- so the right-hand side is all-gathered and every rank solves redundantly)
 	long row = 0, slot = 0;
 	for (Batch &b : ctx->batches) {
 		if (b.type == BT_COLLISION) { b.perm = ctx->node_perm; }
@@ -427,6 +439,7 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		ADMMB_CUDA(ctx, ctx->d_bad.alloc(1));
 		ADMMB_CUDA(ctx, ctx->d_bad.zero(s));
 		ADMMB_CUDA(ctx, ctx->d_io.alloc(6 * (size_t)n));
+		if (ctx->h_pin) { cudaFreeHost(ctx->h_pin); ctx->h_pin = nullptr; } // a retry after a failed finalize
 		ADMMB_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, 6 * (size_t)n * sizeof(double)));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
 	}
@@ -467,6 +480,28 @@ static void drop_iteration_graph(admmb_ctx *ctx) {
 	}
 }
 
+// Right-hand side (System.cpp:61).  On a mesh partitioned over ranks every rank has evaluated the forces that touch its own
+// nodes, so its OWN rows of b are complete (and bit-identical to the single-GPU sum: same slots, same order); with the
+// direct solver, which every rank runs redundantly on the whole vector, the owned chunks are all-gathered in place
+// (NCCL over NVLink, 3n doubles per ADMM iteration: 4.2 MB at 1 M tets).  PCG only needs the owned rows.
+static int rhs_phase(admmb_ctx *ctx) {
+	int rc = launch_rhs(ctx);
+	if (rc) return rc;
+	if (ctx->dist_world > 1 && ctx->solver == ADMMB_SOLVER_DIRECT) rc = dist_allgather_nodes(ctx, ctx->d_b.p);
+	return rc;
+}
+// Solve (System.cpp:62).  The replicated direct solve accumulates with floating-point atomics by default, so the ranks'
+// solutions agree only to rounding; every rank therefore keeps ITS chunk and the chunks are all-gathered: all ranks hold
+// the same curr_x bit for bit (a boundary force evaluated on two ranks sees identical inputs), for 20 us per iteration.
+// With the deterministic solve the ranks' solutions are already identical and the exchange is skipped.
+static int solve_phase(admmb_ctx *ctx) {
+	if (ctx->solver == ADMMB_SOLVER_PCG) return pcg_solve(ctx);
+	int rc = direct_solve(ctx);
+	if (rc) return rc;
+	if (ctx->dist_world > 1 && !ctx->deterministic) rc = dist_allgather_nodes(ctx, ctx->d_currx.p);
+	return rc;
+}
+
 // One ADMM iteration (System.cpp:51-66): local step of every batch, right-hand side, solve.
 static int enqueue_iteration(admmb_ctx *ctx) {
 	const double dt2 = ctx->dt * ctx->dt;
@@ -474,9 +509,9 @@ static int enqueue_iteration(admmb_ctx *ctx) {
 		int rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
 		if (rc) return rc;
 	}
-	int rc = launch_rhs(ctx);
+	int rc = rhs_phase(ctx);
 	if (rc) return rc;
-	return (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_solve(ctx) : direct_solve(ctx);
+	return solve_phase(ctx);
 }
 
 static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump = nullptr) {
@@ -490,11 +525,20 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 			ADMMB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
 			int rc = enqueue_iteration(ctx);
 			cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->iter_graph);
-			if (rc) { drop_iteration_graph(ctx); return rc; }
-			ADMMB_CUDA(ctx, e);
-			ADMMB_CUDA(ctx, cudaGraphInstantiate(&ctx->iter_graph_exec, ctx->iter_graph, 0));
+			if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&ctx->iter_graph_exec, ctx->iter_graph, 0);
 			ctx->iter_graph_launches = ctx->launches - before;
 			ctx->launches = before;
+			if (rc || e != cudaSuccess) {
+				drop_iteration_graph(ctx);
+				cudaGetLastError();
+				if (ctx->dist_world > 1) {
+					// the collectives of a partitioned mesh could not be captured (NCCL build without graph support): plain launches
+					ctx->use_graph = false;
+					return run_iterations(ctx, admm_iters, dump);
+				}
+				if (rc) return rc;
+				ADMMB_CUDA(ctx, e);
+			}
 		}
 		for (int it = 0; it < admm_iters; ++it) ADMMB_CUDA(ctx, cudaGraphLaunch(ctx->iter_graph_exec, ctx->stream));
 		ctx->launches += ctx->iter_graph_launches * admm_iters;
@@ -503,20 +547,27 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 	// Timed mode with the direct solver: the three phases are captured as three small graphs so that the per-phase
 	// event timings see the same launch behaviour as the production path (one graph per iteration).
 	if (timed && !dump && ctx->use_graph && ctx->solver == ADMMB_SOLVER_DIRECT) {
-		if (!ctx->phase_graph_exec[0]) {
+		if (!(ctx->phase_graph_exec[0] && ctx->phase_graph_exec[1] && ctx->phase_graph_exec[2])) {
 			const long before = ctx->launches;
 			for (int ph = 0; ph < 3; ++ph) {
 				cudaGraph_t g = nullptr;
 				ADMMB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
 				int rc = ADMMB_OK;
 				if (ph == 0) { for (Batch &b : ctx->batches) if ((rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2))) break; }
-				else if (ph == 1) rc = launch_rhs(ctx);
-				else rc = direct_solve(ctx);
+				else if (ph == 1) rc = rhs_phase(ctx);
+				else rc = solve_phase(ctx);
 				cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-				if (rc) return rc;
-				ADMMB_CUDA(ctx, e);
-				ADMMB_CUDA(ctx, cudaGraphInstantiate(&ctx->phase_graph_exec[ph], g, 0));
-				cudaGraphDestroy(g);
+				if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&ctx->phase_graph_exec[ph], g, 0);
+				if (g) cudaGraphDestroy(g);
+				if (rc || e != cudaSuccess) {
+					// no half-built set of phase graphs may survive: the next timed step would launch a null graph
+					drop_iteration_graph(ctx);
+					ctx->launches = before;
+					cudaGetLastError();
+					if (ctx->dist_world > 1) { ctx->use_graph = false; return run_iterations(ctx, admm_iters, dump); }
+					if (rc) return rc;
+					ADMMB_CUDA(ctx, e);
+				}
 			}
 			ctx->iter_graph_launches = ctx->launches - before;
 			ctx->launches = before;
@@ -550,10 +601,10 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 			if (rc) return rc;
 		}
 		if (timed) next_event(ctx);
-		int rc = launch_rhs(ctx);
+		int rc = rhs_phase(ctx);
 		if (rc) return rc;
 		if (timed) next_event(ctx);
-		rc = (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_solve(ctx) : direct_solve(ctx);
+		rc = solve_phase(ctx);
 		if (rc) return rc;
 		if (timed) next_event(ctx);
 	}
@@ -621,6 +672,7 @@ extern "C" int admmb_unregister_host_buffer(admmb_ctx *ctx, void *ptr) {
 
 extern "C" int admmb_upload_xv(admmb_ctx *ctx, const double *x3n, const double *v3n) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "upload_xv");
 	const size_t n3 = 3 * (size_t)ctx->n;
 	cudaStream_t s = ctx->stream;
 	const double *src[2] = { x3n, v3n };
@@ -668,6 +720,7 @@ static void finish_download(admmb_ctx *ctx) {
 
 extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "download_xv");
 	int rc = enqueue_download(ctx, x3n, v3n);
 	if (rc) return rc;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -677,6 +730,7 @@ extern "C" int admmb_download_xv(admmb_ctx *ctx, double *x3n, double *v3n) {
 
 extern "C" int admmb_download_x_f32(admmb_ctx *ctx, float *x3n) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "download_x_f32");
 	if (!x3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "download_x_f32: null output");
 	const size_t n3 = 3 * (size_t)ctx->n;
 	float *d_tmp = reinterpret_cast<float *>(ctx->d_io.p);
@@ -692,6 +746,7 @@ extern "C" int admmb_download_x_f32(admmb_ctx *ctx, float *x3n) {
 
 extern "C" int admmb_step(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "step");
 	if (admm_iters < 0 || !x3n_inout || !v3n_inout) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step: bad arguments");
 	const bool timed = ctx->timing.on;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -715,7 +770,13 @@ extern "C" int admmb_step_async(admmb_ctx *ctx, int admm_iters, double *x3n_inou
 	int rc = admmb_upload_xv(ctx, x3n_inout, v3n_inout);
 	if (rc) return rc;
 	if ((rc = launch_frame_begin(ctx))) return rc;
-	if ((rc = run_iterations(ctx, admm_iters))) return rc;
+	// phase timing is collected by the synchronous calls only: an asynchronous step records no events (the pool would
+	// otherwise grow by 4 events per iteration and call, never reset)
+	const bool timing_was_on = ctx->timing.on;
+	ctx->timing.on = false;
+	rc = run_iterations(ctx, admm_iters);
+	ctx->timing.on = timing_was_on;
+	if (rc) return rc;
 	if ((rc = launch_frame_end(ctx))) return rc;
 	ctx->elapsed_s += ctx->dt;
 	return enqueue_download(ctx, x3n_inout, v3n_inout);
@@ -724,6 +785,7 @@ extern "C" int admmb_step_async(admmb_ctx *ctx, int admm_iters, double *x3n_inou
 extern "C" int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout, double *v3n_inout, double *x_it, double *z_it,
                                double *u_it) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "step_dump");
 	if (admm_iters < 0 || !x3n_inout || !v3n_inout) ADMMB_FAIL(ctx, ADMMB_E_ARG, "step_dump: bad arguments");
 	DumpTarget d = { x_it, z_it, u_it };
 	int rc = admmb_upload_xv(ctx, x3n_inout, v3n_inout);
@@ -738,6 +800,7 @@ extern "C" int admmb_step_dump(admmb_ctx *ctx, int admm_iters, double *x3n_inout
 // Diagnostics for "teacher-forced" parity tests: run exactly one half of an ADMM iteration on given inputs.
 extern "C" int admmb_debug_local_step(admmb_ctx *ctx, const double *x3n) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "debug_local_step");
 	if (!x3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null x");
 	const size_t n3 = 3 * (size_t)ctx->n;
 	memcpy(ctx->h_pin, x3n, n3 * sizeof(double));
@@ -752,6 +815,7 @@ extern "C" int admmb_debug_local_step(admmb_ctx *ctx, const double *x3n) {
 
 extern "C" int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "debug_global_step");
 	if (!xbar3n) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null x_bar");
 	const size_t n3 = 3 * (size_t)ctx->n;
 	// M x_bar on the host exactly as System.cpp:47 (m_masses.asDiagonal() * x_bar), then permuted in
@@ -760,8 +824,8 @@ extern "C" int admmb_debug_global_step(admmb_ctx *ctx, const double *xbar3n) {
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p, ctx->h_pin, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	int rc = launch_permute_in(ctx, ctx->d_io.p, ctx->d_Mxbar.p);
 	if (rc) return rc;
-	if ((rc = launch_rhs(ctx))) return rc;
-	rc = (ctx->solver == ADMMB_SOLVER_PCG) ? pcg_solve(ctx) : direct_solve(ctx);
+	if ((rc = rhs_phase(ctx))) return rc;
+	rc = solve_phase(ctx);
 	if (rc) return rc;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ADMMB_OK;
@@ -884,13 +948,22 @@ extern "C" int admmb_get_batch_weights(admmb_ctx *ctx, int batch, double *weight
 }
 
 extern "C" int admmb_recompute_weights(admmb_ctx *ctx) {
-	CHECK_READY(ctx);
+	CHECK_CTX(ctx);
+	if (!ctx->finalized) ADMMB_FAIL(ctx, ADMMB_E_STATE, "admmb_finalize has not been called");
+	CHECK_NO_PENDING(ctx, "recompute_weights");
 	drop_iteration_graph(ctx); // weight arrays and the factor are re-allocated
+	// Until BOTH the weight arrays and the factor are those of the new weights the context must not step: a failure in
+	// between (e.g. weights that make the matrix indefinite) would otherwise leave right-hand-side weights and factor tiles
+	// of different systems behind.  A later successful call repairs it.
+	ctx->broken = true;
 	for (Batch &b : ctx->batches) {
 		int rc = upload_batch_weights(ctx, b);
 		if (rc) return rc;
 	}
-	return setup_solver(ctx);
+	int rc = setup_solver(ctx);
+	if (rc) return rc;
+	ctx->broken = false;
+	return ADMMB_OK;
 }
 
 // ---- state access -----------------------------------------------------------------------------------------
@@ -910,6 +983,9 @@ extern "C" long admmb_state_size(admmb_ctx *ctx, int which) {
 }
 
 static int soa_download(admmb_ctx *ctx, const Batch &b, const double *d, int ncomp, double *out_aos) {
+	// a mesh partitioned over ranks: this rank holds only the forces that touch its nodes; the entries of the others are
+	// NaN here (merge the ranks' exports by taking the non-NaN entries; duplicated boundary forces are bit-identical)
+	if (b.nlocal < b.count) std::fill(out_aos, out_aos + (size_t)ncomp * b.count, std::nan(""));
 	std::vector<double> soa((size_t)ncomp * b.nlocal);
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(soa.data(), d, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -929,6 +1005,7 @@ static int soa_upload(admmb_ctx *ctx, const Batch &b, double *d, int ncomp, cons
 
 extern "C" int admmb_get_state(admmb_ctx *ctx, int which, double *out) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "get_state");
 	if (!out) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null output");
 	int rc;
 	switch (which) {
@@ -960,6 +1037,7 @@ extern "C" int admmb_get_state(admmb_ctx *ctx, int which, double *out) {
 		for (const Batch &b : ctx->batches) {
 			if (!is_hyper(b) || b.count == 0) continue;
 			std::vector<int> its(b.nlocal);
+			if (b.nlocal < b.count) std::fill(out + o, out + o + b.count, std::nan("")); // partitioned mesh: see soa_download
 			ADMMB_CUDA(ctx, cudaMemcpyAsync(its.data(), b.d_its.p, its.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 			ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			for (int p = 0; p < b.nlocal; ++p) out[o + b.perm[p]] = (double)its[p];
@@ -973,6 +1051,7 @@ extern "C" int admmb_get_state(admmb_ctx *ctx, int which, double *out) {
 
 extern "C" int admmb_set_state(admmb_ctx *ctx, int which, const double *in) {
 	CHECK_READY(ctx);
+	CHECK_NO_PENDING(ctx, "set_state");
 	if (!in) ADMMB_FAIL(ctx, ADMMB_E_ARG, "null input");
 	int rc;
 	switch (which) {

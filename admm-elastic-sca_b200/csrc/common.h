@@ -85,6 +85,7 @@ struct Batch {
 // Explicit forces applied on the device at the start of every frame, in registration order (System.cpp:37-39).
 struct ExplicitEntry {
 	int kind = 0;                 // 0 ExplicitForce over all nodes, 1 ExplicitForce over a node subset, 2 WindForce
+	bool enabled = true;          // admmb_enable_explicit
 	double dir[3] = { 0, 0, 0 };
 	std::vector<int> idx;         // kind 1: user node ids; kind 2: 3 user node ids per triangle, reference order
 	int count = 0;                // nodes / triangles
@@ -112,6 +113,7 @@ struct admmb_ctx {
 	cudaStream_t stream = nullptr;
 	std::string err;
 	bool finalized = false;
+	bool broken = false;        // a refactorisation failed after the new weights were uploaded: factor and weights disagree
 
 	int n = 0;
 	double dt = 0.0;

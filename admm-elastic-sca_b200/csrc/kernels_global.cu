@@ -91,14 +91,16 @@ int launch_frame_begin(admmb_ctx *ctx) {
 	// Explicit forces run in registration order (System.cpp:37-39).  The common case -- a few plain ExplicitForces --
 	// is folded into the frame kernel; anything else (node subsets, wind) gets its own launch, in order.
 	bool plain = ctx->explicit_forces.size() <= 8;
-	for (const ExplicitEntry &e : ctx->explicit_forces) plain = plain && e.kind == 0;
+	for (const ExplicitEntry &e : ctx->explicit_forces) plain = plain && (e.kind == 0 || !e.enabled);
 	if (plain) {
 		for (const ExplicitEntry &e : ctx->explicit_forces) {
+			if (!e.enabled) continue;
 			for (int j = 0; j < 3; ++j) G.g[G.count][j] = e.dir[j];
 			G.count++;
 		}
 	} else {
 		for (ExplicitEntry &e : ctx->explicit_forces) {
+			if (!e.enabled) continue;
 			int rc = launch_explicit(ctx, e);
 			if (rc) return rc;
 		}

@@ -27,6 +27,7 @@ namespace admmb {
 #ifndef HYPER_THREADS
 #define HYPER_THREADS 320
 #endif
+#define PARK_SLOTS 18 // per thread: U and V of the SVD while the optimiser runs (local_bodies.h)
 #ifndef HYPER_MIN_BLOCKS
 #define HYPER_MIN_BLOCKS 2
 #endif
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(LOCAL_THREADS) k_local_tets(const LocalArgs a)
 // hyperelastic tets: U, V of the SVD are parked in shared memory while the optimiser runs (local_bodies.h)
 template <class Model, int MH>
 __global__ void __launch_bounds__(HYPER_THREADS, HYPER_MIN_BLOCKS) k_local_tets_hyper(const LocalArgs a) {
-	__shared__ double park[18 * HYPER_THREADS];
+	extern __shared__ double park[]; // PARK_SLOTS * HYPER_THREADS doubles (dynamic: more than the 48 KB a static array may have)
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e < a.count) local_tet_hyper<Model, MH>(a, e, park + threadIdx.x, HYPER_THREADS);
 }
@@ -65,9 +66,26 @@ __global__ void __launch_bounds__(LOCAL_THREADS) k_local_collision(const LocalAr
 	if (e < a.count) local_collision(a, e);
 }
 
+#define HYPER_SMEM (PARK_SLOTS * HYPER_THREADS * sizeof(double))
+// the hyperelastic kernels park more than the default 48 KB of dynamic shared memory per block: opt in, once per device
+static int hyper_smem_opt_in(admmb_ctx *ctx) {
+	static bool done[64] = { false };
+	if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return ADMMB_OK;
+	ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_local_tets_hyper<NHModel, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYPER_SMEM));
+	ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_local_tets_hyper<NHModel, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYPER_SMEM));
+	ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_local_tets_hyper<StVKModel, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYPER_SMEM));
+	ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_local_tets_hyper<StVKModel, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HYPER_SMEM));
+	if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
+	return ADMMB_OK;
+}
+
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 	(void)dt2;
 	if (b.nlocal == 0) return ADMMB_OK;
+	if (b.type == BT_TETS && (b.kind == ADMMB_TET_NEOHOOKEAN || b.kind == ADMMB_TET_STVK)) {
+		int rc = hyper_smem_opt_in(ctx);
+		if (rc) return rc;
+	}
 	LocalArgs a;
 	memset(&a, 0, sizeof(a));
 	a.count = b.nlocal;
@@ -87,14 +105,14 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 		case ADMMB_TET_VOLUME: k_local_tets<ADMMB_TET_VOLUME, 1><<<grid, LOCAL_THREADS, 0, s>>>(a); break;
 		case ADMMB_TET_NEOHOOKEAN: {
 			const int g = (b.nlocal + HYPER_THREADS - 1) / HYPER_THREADS;
-			if (b.max_iterations <= 5) k_local_tets_hyper<NHModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
-			else k_local_tets_hyper<NHModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
+			if (b.max_iterations <= 5) k_local_tets_hyper<NHModel, 5><<<g, HYPER_THREADS, HYPER_SMEM, s>>>(a);
+			else k_local_tets_hyper<NHModel, 10><<<g, HYPER_THREADS, HYPER_SMEM, s>>>(a);
 			break;
 		}
 		case ADMMB_TET_STVK: {
 			const int g = (b.nlocal + HYPER_THREADS - 1) / HYPER_THREADS;
-			if (b.max_iterations <= 5) k_local_tets_hyper<StVKModel, 5><<<g, HYPER_THREADS, 0, s>>>(a);
-			else k_local_tets_hyper<StVKModel, 10><<<g, HYPER_THREADS, 0, s>>>(a);
+			if (b.max_iterations <= 5) k_local_tets_hyper<StVKModel, 5><<<g, HYPER_THREADS, HYPER_SMEM, s>>>(a);
+			else k_local_tets_hyper<StVKModel, 10><<<g, HYPER_THREADS, HYPER_SMEM, s>>>(a);
 			break;
 		}
 		}

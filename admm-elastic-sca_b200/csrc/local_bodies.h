@@ -48,6 +48,7 @@ ADMMB_HD void tet_load_Dx(const LocalArgs &a, const int e, double *B, double *Dx
 #pragma unroll
 		for (int j = 0; j < 3; ++j)
 			Dx[3 * r + j] = ((B[0 * 3 + r] * xs[0][j] + B[1 * 3 + r] * xs[1][j]) + B[2 * 3 + r] * xs[2][j]) + B[3 * 3 + r] * xs[3][j];
+	ADMMB_FLOPS(9 * 7);
 }
 
 // u += D_i x - z, store u and z, and this force's share of the right-hand side dt^2 D_i^T W_i^2 (z - u).
@@ -68,6 +69,7 @@ ADMMB_HD void tet_finish(const LocalArgs &a, const int e, const double *B, const
 #pragma unroll
 		for (int j = 0; j < 3; ++j)
 			P[3 * v + j] = c * ((B[v * 3 + 0] * zu[j] + B[v * 3 + 1] * zu[3 + j]) + B[v * 3 + 2] * zu[6 + j]);
+	ADMMB_FLOPS(9 * 3 + 12 * 6);
 }
 
 // LinearTetStrain / TetVolume: closed-form projection, everything stays in registers.
@@ -99,6 +101,7 @@ ADMMB_HD void local_tet_hyper(const LocalArgs &a, const int e, double *park, con
 		tet_load_Dx(a, e, B, q);
 #pragma unroll
 		for (int k = 0; k < 9; ++k) q[k] = q[k] + a.u[(size_t)k * n + e];
+		ADMMB_FLOPS(9);
 		oriented_svd3(q, U, P.s0, V);
 #pragma unroll
 		for (int k = 0; k < 9; ++k) { park[k * ps] = U[k]; park[(9 + k) * ps] = V[k]; }
@@ -121,6 +124,7 @@ ADMMB_HD void local_tet_hyper(const LocalArgs &a, const int e, double *park, con
 	}
 	double B[12], Dx[9], u[9];
 	tet_load_Dx(a, e, B, Dx);
+	ADMMB_FLOPS(-9 * 7); // D_i x is re-formed here only to keep it out of registers during the optimiser: counted once
 #pragma unroll
 	for (int k = 0; k < 9; ++k) u[k] = a.u[(size_t)k * n + e];
 	tet_finish(a, e, B, Dx, u, z);

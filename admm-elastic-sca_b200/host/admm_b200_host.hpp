@@ -12,8 +12,11 @@
 //    subclass unknown to the device is a hard error (no CPU fallback).
 //  * Force::weight / rest-shape members are filled in by System::initialize() from the values the device
 //    library computed (same formulas as the reference's Force::initialize bodies, csrc/rest_state.cpp).
-//  * ExplicitForce::project / WindForce::project run on the host exactly as in the reference (they are per-frame,
-//    user-subclassable and order dependent); x and v cross PCIe once per step().
+//  * The reference's own explicit forces (ExplicitForce over all nodes or a subset, WindForce) run ON THE DEVICE
+//    (admmb_set_gravity / admmb_add_explicit_subset / admmb_add_wind; their `direction` is re-read every step, as
+//    windyflag.cpp:150 changes it per frame).  A user-defined subclass of ExplicitForce cannot run there: if the list
+//    holds one -- or was edited after initialize() -- EVERY explicit force runs on the host in list order through its own
+//    project(), exactly as in the reference, and the device copies are switched off (no reordering, no double application).
 //
 // Needs Eigen (the reference vendors 3.2.5 under A/deps/Eigen3; any 3.x works): only VectorXd / Vector3d /
 // Vector4d / Matrix types appear in the interface.
@@ -31,6 +34,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "../../include/admm_b200.h"
@@ -372,24 +376,43 @@ public:
 	bool step();
 	void recompute_weights();
 
+	// The names of the later admm-elastic releases (`admm::Solver`, add_force): thin aliases of the members above.
+	void add_force(std::shared_ptr<Force> f) { forces.push_back(f); }
+	void add_explicit_force(std::shared_ptr<ExplicitForce> f) { explicit_forces.push_back(f); }
+
 	admmb_ctx *b200_context() { return ctx; } // (new) for state dumps / timing through the C ABI
 
 protected:
 	bool initialized;
 	admmb_ctx *ctx;
-	double *pinned[2] = { 0, 0 }; // storage of m_x / m_v currently page-locked (Settings::pin_host)
+	// storage of m_x / m_v currently page-locked in `ctx` (Settings::pin_host), keyed on (pointer, bytes).  Eigen frees the
+	// old block when it reallocates, so a stale entry is unregistered BEFORE anything else touches it and never
+	// dereferenced; a new context starts with nothing registered (admmb_destroy unregistered what the old one held).
+	double *pinned[2] = { 0, 0 };
+	long pinned_bytes[2] = { 0, 0 };
 	void pin_state() {
-		// Eigen may have reallocated m_x / m_v since the last step (resize): follow the storage
 		double *cur[2] = { m_x.data(), m_v.data() };
 		const long bytes[2] = { (long)(m_x.size() * sizeof(double)), (long)(m_v.size() * sizeof(double)) };
 		for (int k = 0; k < 2; ++k) {
-			if (!settings.pin_host || cur[k] == pinned[k]) continue;
+			if (!settings.pin_host || (cur[k] == pinned[k] && bytes[k] == pinned_bytes[k])) continue;
 			if (pinned[k]) admmb_unregister_host_buffer(ctx, pinned[k]);
-			pinned[k] = (admmb_register_host_buffer(ctx, cur[k], bytes[k]) == 0) ? cur[k] : 0; // failure: staged path
+			const bool ok = admmb_register_host_buffer(ctx, cur[k], bytes[k]) == 0; // failure: staged path
+			pinned[k] = ok ? cur[k] : 0;
+			pinned_bytes[k] = ok ? bytes[k] : 0;
 		}
 	}
-	struct BatchRef { int id; Force::B200Class cls; size_t first, count; };
+	struct BatchRef { int id; Force::B200Class cls; size_t first, count; std::vector<double> pos; std::vector<int> act; bool any_inactive; };
 	std::vector<BatchRef> batches;
+	// explicit forces as registered on the device at initialize(): the object, its device id and the direction last sent
+	struct ExplicitRef { const ExplicitForce *obj; int id; double dir[3]; };
+	std::vector<ExplicitRef> device_explicit;
+	bool explicit_on_host = false;
+	bool explicit_list_unchanged() const {
+		if (device_explicit.size() != explicit_forces.size()) return false;
+		for (size_t i = 0; i < device_explicit.size(); ++i)
+			if (device_explicit[i].obj != explicit_forces[i].get()) return false;
+		return true;
+	}
 	bool fail(const char *what) {
 		std::cerr << "\n**Solver Error: " << what << ": " << admmb_last_error(ctx) << std::endl;
 		return false;
@@ -409,6 +432,8 @@ inline bool System::initialize() {
 	if (m_v.size() < m_x.size()) m_v.resize(m_x.size());
 	m_v.setZero();
 	if (ctx) { admmb_destroy(ctx); ctx = 0; }
+	pinned[0] = pinned[1] = 0; // the destroyed context unregistered its buffers
+	pinned_bytes[0] = pinned_bytes[1] = 0;
 	if (admmb_create(settings.device, &ctx) != ADMMB_OK) {
 		std::cerr << "\n**Solver Error: " << admmb_last_error(0) << std::endl;
 		return false;
@@ -496,10 +521,35 @@ inline bool System::initialize() {
 			for (size_t k = i; k < j; ++k) w[k - i] = forces[k]->weight;
 			admmb_set_batch_weights(ctx, id, w.data());
 		}
-		BatchRef br = { id, f0->b200_class(), i, (size_t)cnt };
+		BatchRef br;
+		br.id = id; br.cls = f0->b200_class(); br.first = i; br.count = (size_t)cnt; br.any_inactive = false;
+		if (br.cls == Force::B_MOVING_ANCHOR) { // what the device holds: the positions just sent, all active
+			br.pos.resize(3 * (size_t)cnt);
+			br.act.assign(cnt, 1);
+			for (size_t k = i; k < j; ++k)
+				for (int c = 0; c < 3; ++c) br.pos[3 * (k - i) + c] = static_cast<const MovingAnchor *>(forces[k].get())->point->pos[c];
+		}
 		batches.push_back(br);
 		for (size_t k = i; k < j; ++k) { forces[k]->global_idx = (int)row; row += forces[k]->b200_rows(); }
 		i = j;
+	}
+	// explicit forces: the reference's own classes go to the device, in list order; one unknown subclass keeps all on the host
+	device_explicit.clear();
+	explicit_on_host = false;
+	for (size_t e = 0; e < explicit_forces.size(); ++e) {
+		const ExplicitForce *f = explicit_forces[e].get();
+		if (!(typeid(*f) == typeid(ExplicitForce) || typeid(*f) == typeid(WindForce))) explicit_on_host = true;
+	}
+	for (size_t e = 0; e < explicit_forces.size() && !explicit_on_host; ++e) {
+		const ExplicitForce *f = explicit_forces[e].get();
+		ExplicitRef r;
+		r.obj = f;
+		for (int c = 0; c < 3; ++c) r.dir[c] = f->direction[c];
+		if (const WindForce *w = dynamic_cast<const WindForce *>(f)) r.id = admmb_add_wind(ctx, (int)(w->tris.size() / 3), w->tris.data(), r.dir);
+		else if (f->indices.empty()) r.id = admmb_set_gravity(ctx, -1, r.dir);
+		else r.id = admmb_add_explicit_subset(ctx, (int)f->indices.size(), f->indices.data(), r.dir);
+		if (r.id < 0) return fail("explicit forces");
+		device_explicit.push_back(r);
 	}
 	if (admmb_finalize(ctx, settings.timestep_s) < 0) return fail("finalize");
 	// read back the weights the library computed (Force::initialize in the reference)
@@ -521,29 +571,51 @@ inline bool System::step() {
 	for (size_t cb = 0; cb < pre_step_callbacks.size(); ++cb) pre_step_callbacks[cb](this);
 	if (!initialized || !ctx) return false;
 	const double dt = settings.timestep_s;
-	for (size_t i = 0; i < explicit_forces.size(); ++i) explicit_forces[i]->project(dt, m_x, m_v, m_masses);
-	// control points are owned by the caller and may have moved / been released since the last step
-	for (size_t b = 0; b < batches.size(); ++b) {
-		if (batches[b].cls != Force::B_MOVING_ANCHOR) continue;
-		std::vector<double> pos(3 * batches[b].count);
-		std::vector<int> act(batches[b].count);
-		for (size_t k = 0; k < batches[b].count; ++k) {
-			const MovingAnchor *a = static_cast<const MovingAnchor *>(forces[batches[b].first + k].get());
-			for (int c = 0; c < 3; ++c) pos[3 * k + c] = a->point->pos[c];
-			act[k] = a->point->active ? 1 : 0;
+	// explicit forces (System.cpp:37-39): on the device unless the list holds a user subclass or was edited since initialize()
+	if (!explicit_on_host && !explicit_list_unchanged()) {
+		for (size_t e = 0; e < device_explicit.size(); ++e) admmb_enable_explicit(ctx, device_explicit[e].id, 0);
+		explicit_on_host = true;
+	}
+	if (explicit_on_host) {
+		for (size_t i = 0; i < explicit_forces.size(); ++i) explicit_forces[i]->project(dt, m_x, m_v, m_masses);
+	} else {
+		for (size_t e = 0; e < device_explicit.size(); ++e) { // `direction` is a public member callers change between steps
+			ExplicitRef &r = device_explicit[e];
+			const Eigen::Vector3d &d = r.obj->direction;
+			if (d[0] == r.dir[0] && d[1] == r.dir[1] && d[2] == r.dir[2]) continue;
+			for (int c = 0; c < 3; ++c) r.dir[c] = d[c];
+			if (admmb_set_gravity(ctx, r.id, r.dir) < 0) return fail("explicit force direction");
 		}
-		if (admmb_update_anchor_targets(ctx, batches[b].id, 0, (int)batches[b].count, pos.data(), act.data()) < 0) return fail("anchor targets");
+	}
+	// control points are owned by the caller and may have moved / been released since the last step: sent when they changed
+	for (size_t b = 0; b < batches.size(); ++b) {
+		BatchRef &B = batches[b];
+		if (B.cls != Force::B_MOVING_ANCHOR) continue;
+		bool changed = false;
+		B.any_inactive = false;
+		for (size_t k = 0; k < B.count; ++k) {
+			const MovingAnchor *a = static_cast<const MovingAnchor *>(forces[B.first + k].get());
+			const int act = a->point->active ? 1 : 0;
+			for (int c = 0; c < 3; ++c)
+				if (B.pos[3 * k + c] != a->point->pos[c]) { B.pos[3 * k + c] = a->point->pos[c]; changed = true; }
+			if (B.act[k] != act) { B.act[k] = act; changed = true; }
+			B.any_inactive = B.any_inactive || !act;
+		}
+		if (changed && admmb_update_anchor_targets(ctx, B.id, 0, (int)B.count, B.pos.data(), B.act.data()) < 0) return fail("anchor targets");
 	}
 	pin_state();
 	if (admmb_step(ctx, settings.admm_iters, m_x.data(), m_v.data()) < 0) return fail("step");
-	// inactive control points follow the mesh (MovingAnchor::project writes point->pos, AnchorForce.cpp:82)
+	// inactive control points follow the mesh (MovingAnchor::project writes point->pos, AnchorForce.cpp:82): read back only then
 	for (size_t b = 0; b < batches.size(); ++b) {
-		if (batches[b].cls != Force::B_MOVING_ANCHOR) continue;
-		std::vector<double> pos(3 * batches[b].count);
-		if (admmb_get_anchor_targets(ctx, batches[b].id, 0, (int)batches[b].count, pos.data(), 0) < 0) return fail("anchor targets");
-		for (size_t k = 0; k < batches[b].count; ++k) {
-			MovingAnchor *a = static_cast<MovingAnchor *>(forces[batches[b].first + k].get());
-			if (!a->point->active) a->point->pos = Eigen::Vector3d(pos[3 * k], pos[3 * k + 1], pos[3 * k + 2]);
+		BatchRef &B = batches[b];
+		if (B.cls != Force::B_MOVING_ANCHOR || !B.any_inactive) continue;
+		std::vector<double> pos(3 * B.count);
+		if (admmb_get_anchor_targets(ctx, B.id, 0, (int)B.count, pos.data(), 0) < 0) return fail("anchor targets");
+		for (size_t k = 0; k < B.count; ++k) {
+			MovingAnchor *a = static_cast<MovingAnchor *>(forces[B.first + k].get());
+			if (a->point->active) continue;
+			a->point->pos = Eigen::Vector3d(pos[3 * k], pos[3 * k + 1], pos[3 * k + 2]);
+			for (int c = 0; c < 3; ++c) B.pos[3 * k + c] = pos[3 * k + c]; // the device already holds this value
 		}
 	}
 	elapsed_s += dt;
@@ -561,6 +633,9 @@ inline void System::recompute_weights() {
 	}
 	if (admmb_recompute_weights(ctx) < 0) fail("recompute_weights");
 }
+
+// `admm::Solver` is what the later releases of the library call this class (BASELINE.json north_star uses that name).
+typedef System Solver;
 
 } // namespace admm
 

@@ -18,11 +18,20 @@
 
 using namespace admm;
 
+// a user-defined ExplicitForce subclass (what the reference lets callers write): cannot run on the device, so its
+// presence makes the host layer apply EVERY explicit force on the host in list order (argv[3] == "userforce")
+class UserGravity : public ExplicitForce {
+public:
+	UserGravity(Eigen::Vector3d d) : ExplicitForce(d) {}
+	void project(double dt, Eigen::VectorXd &x, Eigen::VectorXd &v, Eigen::VectorXd &m) const { ExplicitForce::project(dt, x, v, m); }
+};
+
 int main(int argc, char **argv) {
-	if (argc < 3) { fprintf(stderr, "usage: host_check scene.txt out.bin\n"); return 2; }
+	if (argc < 3) { fprintf(stderr, "usage: host_check scene.txt out.bin [userforce]\n"); return 2; }
+	const bool userforce = argc > 3 && std::string(argv[3]) == "userforce";
 	std::ifstream in(argv[1]);
 	if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
-	System system;
+	Solver system; // the later releases' name of admm::System (alias)
 	system.settings.verbose = 0;
 	int frames, n;
 	in >> system.settings.timestep_s >> system.settings.admm_iters >> frames >> n;
@@ -71,7 +80,7 @@ int main(int argc, char **argv) {
 				cps.push_back(cp);
 				f.reset(new MovingAnchor(i0, cp, p0));
 			} else { fprintf(stderr, "unknown batch type %s\n", type.c_str()); return 2; }
-			system.forces.push_back(f);
+			if (e % 2) system.add_force(f); else system.forces.push_back(f); // add_force: alias of forces.push_back
 		}
 		if (type == "collision") { // count = number of shapes
 			fprintf(stderr, "collision batches use the 'shapes' record\n");
@@ -99,7 +108,8 @@ int main(int argc, char **argv) {
 		std::string type;
 		double dx, dy, dz;
 		in >> type >> dx >> dy >> dz;
-		if (type == "gravity") system.explicit_forces.push_back(std::shared_ptr<ExplicitForce>(new ExplicitForce(Eigen::Vector3d(dx, dy, dz))));
+		if (type == "gravity" && userforce) system.explicit_forces.push_back(std::shared_ptr<ExplicitForce>(new UserGravity(Eigen::Vector3d(dx, dy, dz))));
+		else if (type == "gravity") system.explicit_forces.push_back(std::shared_ptr<ExplicitForce>(new ExplicitForce(Eigen::Vector3d(dx, dy, dz))));
 		else {
 			int nt;
 			in >> nt;

@@ -28,7 +28,7 @@ EXPORTS = [
     "admmb_state_size", "admmb_get_state", "admmb_set_state", "admmb_get_info", "admmb_timing_enable",
     "admmb_timing_read", "admmb_last_region_ms", "admmb_dist_unique_id", "admmb_dist_init",
     "admmb_register_host_buffer", "admmb_unregister_host_buffer", "admmb_download_x_f32", "admmb_set_host_threads", "admmb_step_resident_async", "admmb_sync", "admmb_set_deterministic", "admmb_set_check_finite", "admmb_step_async",
-    "admmb_probe_fp64", "admmb_debug_fastmath_selftest",
+    "admmb_probe_fp64", "admmb_debug_fastmath_selftest", "admmb_enable_explicit",
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
     L.admmb_last_region_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.admmb_dist_unique_id.argtypes = [C.c_char_p]
     L.admmb_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.admmb_enable_explicit.argtypes = [vp, C.c_int, C.c_int]
     L.admmb_probe_fp64.argtypes = [C.c_int, _dp]
     L.admmb_debug_fastmath_selftest.argtypes = [C.c_int, C.c_ulonglong, C.c_long, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")]
     _lib = L
@@ -123,6 +124,29 @@ def fastmath_selftest(samples=1 << 26, seed=1, device=0):
     if rc != 0:
         raise RuntimeError(f"admmb_debug_fastmath_selftest failed ({rc})")
     return out[:4].astype(np.int64), out[4:].astype(np.int64)
+
+
+_flop_lib = None
+
+
+def flopcount_hyper_tets(kind, x_rest, idx, mu, lam, maxit, dt, x_cur, u, state):
+    """Algorithmic FP64 flops of ONE ADMM iteration's local step over the given hyperelastic tets (csrc/flopcount.cpp: the
+    kernels' per-force body compiled for the host with counters; add / mul / div / sqrt / log = 1 flop).  idx [count][4],
+    u [count][9], state [count][4] entering the iteration.  Returns (flops, objective evaluations, L-BFGS iterations)."""
+    global _flop_lib
+    if _flop_lib is None:
+        path = os.path.join(os.path.dirname(_HERE), "libadmm_b200_flopcount.so")
+        _flop_lib = C.CDLL(path)
+        _flop_lib.admmb_flopcount_hyper_tets.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, C.c_double, C.c_double, C.c_int, C.c_double,
+                                                        _dp, _dp, _dp, _dp]
+    idx = _i32(idx).reshape(-1, 4)
+    out = np.zeros(3)
+    x_rest = _f64(x_rest).reshape(-1)
+    rc = _flop_lib.admmb_flopcount_hyper_tets(int(kind), x_rest.size // 3, x_rest, idx.shape[0], idx, float(mu), float(lam), int(maxit), float(dt),
+                                              _f64(x_cur).reshape(-1), _f64(u).reshape(-1), _f64(state).reshape(-1), out)
+    if rc != 0:
+        raise RuntimeError("admmb_flopcount_hyper_tets failed")
+    return float(out[0]), float(out[1]), float(out[2])
 
 
 def _i32(a):

@@ -34,8 +34,12 @@ METRIC = "admm_iterations_per_s_cube_1M_tets"
 UNIT = "ADMM iterations/s"
 ADMM_ITERS = 10
 FULL_TETS = 998250  # N = 55
-EXEC_FP64_FLOPS_PER_TET_ITER = 9301      # profiles/r1e_local.txt (steady state): (1184.0 + 1325.7 + 2 x 1477.5) flops/clk x 1.6991 Mclk / 998250 tets
-SOLVE_DRAM_BYTES_NCU = 1.7221e9          # profiles/r1e_solve.txt: dram bytes read+written by the 26 launches of one solve (cube N=55)
+# The reference's line search only reaches its steady regime (maxfev evaluations in almost every tet) after ~20 frames of
+# the x1.3 stretch excitation: these frames are ALWAYS run, untimed, before the --warmup frames, on every arm, so that
+# `value` does not depend on --warmup.
+CONDITION_FRAMES = 20
+SHIPPED = ("bunnyexpand", "windyflag", "poordillo", "plinkopony")
+LOCAL_BYTES_PER_TET = 608.0   # idx 16 + x gather 96 + B 96 + u r/w 144 + z w 72 + state r/w 64 + weights 24 + P w 96
 
 
 def peaks():
@@ -120,6 +124,97 @@ def make_scene(N):
     return scenes.cube_scene(N, kind=scenes.TET_NH, mu=1e5, lam=1e5, maxit=5, mass=1000.0, dt=0.04, iters=ADMM_ITERS, stretch=1.3)
 
 
+def load_workload(name):
+    """(scene dict, label) for 'cubeN' or one of the reference's shipped scenes (fixtures exported by the reference's own
+    scene layer: tests/golden/shipped_*.scene.npz, oracle/scene_export.cpp)."""
+    import scenes
+    if name.startswith("cube"):
+        N = int(name[4:])
+        sc = make_scene(N)
+        return sc, f"cube N={N} ({sc['batches'][0]['idx'].shape[0]} tets) NeoHookean mu=lambda=1e5 max_iterations=5, {sc['iters']} ADMM iterations per step, x1.3 stretch"
+    sc = scenes.load_scene(os.path.join(ROOT, "tests", "golden", f"shipped_{name}.scene.npz"))
+    nel = sum(len(b["idx"]) for b in sc["batches"] if "idx" in b and b["type"] in ("tets", "tris"))
+    return sc, f"samples/{name} ({nel} elements, {sc['x'].shape[0]} nodes), {sc['iters']} ADMM iterations per step, dt {sc['dt']}, no user interaction"
+
+
+def reference_rate(sc, frames, cond):
+    """ADMM iterations/s of the UNMODIFIED reference (oracle/_ref: Eigen + OpenMP on all host cores) on scene `sc`:
+    `cond` untimed frames, then `frames` timed with std::chrono inside the shim (System::step only)."""
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    ref.lib().ref_set_omp_threads(cores)
+    t0 = time.perf_counter()
+    sim = ref.RefSystem(sc, probe=False)
+    t_init = time.perf_counter() - t0
+    if "x_after_init" in sc:
+        sim.set_x(sc["x_after_init"])
+    for _ in range(cond):
+        sim.step()
+    sec = sim.step_timed(frames)
+    stats = sim.stats()
+    sim.close()
+    return {"it_s": frames * sc["iters"] / sec, "ms_per_frame": 1e3 * sec / frames, "init_s": t_init, "cores": cores, "L_nnz": stats["L_nnz"],
+            "frames": frames, "conditioning_frames": cond}
+
+
+def device_rate(sc, device, frames, cond):
+    """ADMM iterations/s of the CUDA path on scene `sc`: resident (CUDA events on the library's stream) and end to end
+    through admmb_step with page-locked host x / v (host clock), after `cond` untimed frames."""
+    import admm_b200
+    import torch
+    t0 = time.perf_counter()
+    sim = admm_b200.System(sc, device=device, pin_host=True)
+    t_setup = time.perf_counter() - t0
+    if "x_after_init" in sc:
+        sim.set_x(sc["x_after_init"])
+    sim.upload()
+    sim.step_resident(frames=cond)
+    l0 = sim.info()["launches_total"]
+    sim.step_resident(frames=frames)
+    ms = sim.last_region_ms()
+    l1 = sim.info()["launches_total"]
+    sim.download()
+    sim.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        sim.step()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    n3 = sim.n3
+    sim.close()
+    return {"it_s": frames * sc["iters"] / (ms * 1e-3), "ms_per_frame": ms / frames, "e2e_it_s": frames * sc["iters"] / sec, "e2e_ms_per_frame": 1e3 * sec / frames,
+            "launches_per_frame": (l1 - l0) / frames, "setup_s": t_setup, "frames": frames, "conditioning_frames": cond,
+            "h2d_bytes_per_step": 2 * n3 * 8, "d2h_bytes_per_step": 2 * n3 * 8}
+
+
+PAIR_WORKLOADS = SHIPPED + ("cube30",)
+
+
+def pair_frames(name):
+    return (8, CONDITION_FRAMES) if name.startswith("cube") else (60, 10)
+
+
+def same_config_pairs(device, which):
+    """Same workload, same frame counts, both implementations, in this run: the reference on the host cores and the CUDA
+    path on the device.  These are the ratios that are NOT extrapolated (the reference cannot even initialise the 1 M-tet
+    headline mesh in bench time: ~44 min)."""
+    from oracle import ref
+    out = {}
+    for name in which:
+        sc, label = load_workload(name)
+        frames, cond = pair_frames(name)
+        d = device_rate(sc, device, frames, cond)
+        row = {"workload": label, "b200_it_s": d["it_s"], "b200_e2e_it_s": d["e2e_it_s"], "b200_launches_per_frame": d["launches_per_frame"],
+               "frames": frames, "conditioning_frames": cond}
+        if ref.available():
+            r = reference_rate(sc, frames, cond)
+            row.update({"reference_it_s": r["it_s"], "reference_cores": r["cores"], "reference_init_s": r["init_s"], "b200_setup_s": d["setup_s"],
+                        "ratio_resident": d["it_s"] / r["it_s"], "ratio_e2e": d["e2e_it_s"] / r["it_s"], "same_config": True})
+        out[name] = row
+    return out
+
+
 def run_reference(args, rank, world):
     """Times the unmodified reference on the host cores.  Rank 0 only."""
     if rank != 0:
@@ -128,30 +223,40 @@ def run_reference(args, rank, world):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libadmm_ref.so missing (build it where /root/reference exists)"}))
         return
+    if args.scene:
+        # same workload as the b200 arm of --scene: a true same-config line
+        sc, label = load_workload(args.scene)
+        r = reference_rate(sc, args.steps, max(args.warmup, 10))
+        line = {"impl": "reference", "metric": f"admm_iterations_per_s_{args.scene}", "value": r["it_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "shipped scene" if args.scene in SHIPPED else "synthetic", "config": {"workload": label},
+                "cpu_baseline": {"value": r["it_s"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": f"the whole workload, {args.steps} frames; initialize() {r['init_s']:.2f} s not included"},
+                "e2e": {"value": r["it_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
     N = args.ref_cube
     sc = make_scene(N)
     ntets = sc["batches"][0]["idx"].shape[0]
-    cores = os.cpu_count() or 1
-    ref.lib().ref_set_omp_threads(cores)
-    t0 = time.perf_counter()
-    sim = ref.RefSystem(sc, probe=False)
-    t_init = time.perf_counter() - t0
-    sim.set_x(sc["x_after_init"])
-    for _ in range(args.warmup):
-        sim.step()
-    sec = sim.step_timed(args.steps)
-    stats = sim.stats()
-    sim.close()
-    its = args.steps * ADMM_ITERS / sec
+    r = reference_rate(sc, args.steps, CONDITION_FRAMES + args.warmup)
+    its = r["it_s"]
     value = its * ntets / FULL_TETS  # scaled by tet count to the 1M-tet unit (generous: the reference's cost grows superlinearly)
-    sample = (f"cube N={N} ({ntets} tets) stepped {args.steps} frames x {ADMM_ITERS} iterations = {its:.2f} it/s measured, "
-              f"scaled x{ntets}/{FULL_TETS} to the 1M-tet unit; initialize() {t_init:.1f} s not included; L nnz {stats['L_nnz']}")
+    sample = (f"cube N={N} ({ntets} tets) stepped {args.steps} frames x {ADMM_ITERS} iterations after {CONDITION_FRAMES + args.warmup} untimed frames = {its:.2f} it/s measured, "
+              f"scaled x{ntets}/{FULL_TETS} to the 1M-tet unit (the reference needs ~44 min to initialise the 1M-tet mesh itself); initialize() {r['init_s']:.1f} s not included; L nnz {r['L_nnz']}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cube N={args.cube} NeoHookean, {ADMM_ITERS} ADMM iterations per step (reference timed on N={N})"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": f"cube N={args.cube} NeoHookean, {ADMM_ITERS} ADMM iterations per step (reference timed on N={N}, EXTRAPOLATED by tet count; "
+                                   f"measured same-config pairs: `same_config_pairs` of the b200 line)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "measured_same_config": {f"cube{N}": {"workload": load_workload(f"cube{N}")[1], "reference_it_s": its, "frames": args.steps,
+                                                  "conditioning_frames": CONDITION_FRAMES + args.warmup, "cores": r["cores"]}}}
+    if not args.no_pairs:
+        for name in SHIPPED:
+            scs, label = load_workload(name)
+            frames, cond = pair_frames(name)
+            rr = reference_rate(scs, frames, cond)
+            line["measured_same_config"][name] = {"workload": label, "reference_it_s": rr["it_s"], "frames": frames, "conditioning_frames": cond, "cores": rr["cores"]}
     print(json.dumps(line))
 
 
@@ -161,20 +266,28 @@ def cpu_baseline_leg(N):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     sc = make_scene(N)
     ntets = sc["batches"][0]["idx"].shape[0]
-    cores = os.cpu_count() or 1
-    ref.lib().ref_set_omp_threads(cores)
-    t0 = time.perf_counter()
-    sim = ref.RefSystem(sc, probe=False)
-    t_init = time.perf_counter() - t0
-    sim.set_x(sc["x_after_init"])
-    sim.step()
     frames = 8
-    sec = sim.step_timed(frames)
-    sim.close()
-    its = frames * ADMM_ITERS / sec
-    return {"value": its * ntets / FULL_TETS, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"unmodified reference (Eigen + OpenMP, {cores} threads) on cube N={N} ({ntets} tets): {its:.2f} it/s over {frames} frames, "
-                      f"scaled x{ntets}/{FULL_TETS}; initialize() {t_init:.1f} s excluded"}
+    r = reference_rate(sc, frames, CONDITION_FRAMES)
+    return {"value": r["it_s"] * ntets / FULL_TETS, "unit": UNIT, "cores": r["cores"], "kind": "reference",
+            "sample": f"unmodified reference (Eigen + OpenMP, {r['cores']} threads) on cube N={N} ({ntets} tets): {r['it_s']:.2f} it/s over {frames} frames after "
+                      f"{CONDITION_FRAMES} untimed frames, scaled x{ntets}/{FULL_TETS}; initialize() {r['init_s']:.1f} s excluded"}
+
+
+def algorithmic_flops_per_tet(sim, sc, sample=4096, seed=12345):
+    """Algorithmic FP64 flops per tet and ADMM iteration of the local step IN THE REGIME JUST TIMED: a random sample of the
+    run's tets -- current positions, duals and optimiser state downloaded from the device -- goes through the kernels'
+    per-force body compiled for the host with flop counters (csrc/flopcount.cpp; add / mul / div / sqrt / log = 1)."""
+    import admm_b200
+    b = sc["batches"][0]
+    T = b["idx"].shape[0]
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(T, size=min(sample, T), replace=False))
+    sim.download()
+    u = sim.u.reshape(T, 9)[pick]
+    st = sim.prox_state()[pick]
+    flops, evals, its = admm_b200.flopcount_hyper_tets(int(b["kind"]), sc["x"], b["idx"][pick], b["p0"], b["p1"], b["maxit"], sc["dt"], sim.m_x, u, st)
+    return {"flops_per_tet_iteration": flops / len(pick), "objective_evaluations_per_tet_iteration": evals / len(pick),
+            "lbfgs_iterations_per_tet_iteration": its / len(pick), "sampled_tets": int(len(pick))}
 
 
 def run_ensemble(args, rank, world, local_rank, torch, dist, admm_b200):
@@ -264,20 +377,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5, help="untimed frames after the fixed 20 conditioning frames")
     ap.add_argument("--cube", type=int, default=55, help="cube resolution N (N=55: 998,250 tets)")
+    ap.add_argument("--scene", default=None, choices=list(SHIPPED),
+                    help="time one of the reference's shipped scenes instead of the cube (both --impl arms run the SAME workload)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-cube", type=int, default=30, help="cube resolution of the reference arm's bounded sample")
     ap.add_argument("--cpu-cube", type=int, default=20, help="cube resolution of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the same-config reference / b200 pairs (shipped scenes, cube N=30)")
+    ap.add_argument("--pairs", default=",".join(PAIR_WORKLOADS), help="comma-separated workloads of the same-config pairs")
     ap.add_argument("--ensemble", type=int, default=0,
                     help="scene-ensemble mode (BASELINE configs[4] '64-scene ensemble'): this many independent scenes (cube --ens-cube) dealt "
                          "round-robin to the ranks, all scenes of a rank in flight at once on their own streams; prints scene-frames/s")
     ap.add_argument("--ens-cube", type=int, default=20, help="cube resolution of the ensemble scenes (N=20: 48,000 tets)")
     ap.add_argument("--solver", default="direct", choices=["direct", "pcg"])
-    ap.add_argument("--partition", action="store_true",
-                    help="N > 1: ONE mesh partitioned over the ranks (PCG rows + local step, NCCL all-gather / all-reduce) instead of "
-                         "the default scene ensemble; strong scaling")
+    ap.add_argument("--partition", default="auto", choices=["auto", "off", "only", "pcg"],
+                    help="N > 1: besides the scene ensemble (`value`), time ONE mesh partitioned over the ranks (local step partitioned, right-hand "
+                         "side all-gathered, direct solve replicated) and report it as `partition` (strong scaling); 'only' makes it the headline; "
+                         "'pcg' = partitioned Jacobi-PCG rows instead of the replicated direct solve")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -304,51 +422,69 @@ def main():
     if args.ensemble > 0:
         run_ensemble(args, rank, world, local_rank, torch, dist, admm_b200)
         return
-    sc = make_scene(args.cube)
+    if args.scene:
+        sc, label = load_workload(args.scene)
+        metric = f"admm_iterations_per_s_{args.scene}"
+    else:
+        sc, label = load_workload(f"cube{args.cube}")
+        metric = METRIC
+    iters_per_frame = int(sc["iters"])
+    hyper = (not args.scene)
     ntets = sc["batches"][0]["idx"].shape[0]
     nverts = sc["x"].shape[0]
-    dist_arg = None
-    if args.partition and world > 1:
-        args.solver = "pcg"   # sparse triangular solves do not shard (replicas only)
-        holder = [admm_b200.dist_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(holder, src=0)
-        dist_arg = (rank, world, holder[0])
-    t0 = time.perf_counter()
-    sim = admm_b200.System(sc, device=local_rank, solver=admm_b200.SOLVER_DIRECT if args.solver == "direct" else admm_b200.SOLVER_PCG,
-                           cg_tol=1e-10, dist=dist_arg, pin_host=True)
-    t_setup = time.perf_counter() - t0
-    info0 = sim.info()
-    sim.set_x(sc["x_after_init"])
-    sim.upload()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident path: `value` -----------------------------------------------------------------------------
+    def build(dist_arg=None, solver=None):
+        t0 = time.perf_counter()
+        sim = admm_b200.System(sc, device=local_rank, solver=solver if solver is not None else (admm_b200.SOLVER_DIRECT if args.solver == "direct" else admm_b200.SOLVER_PCG),
+                               cg_tol=1e-10, dist=dist_arg, pin_host=True)
+        t = time.perf_counter() - t0
+        if "x_after_init" in sc:
+            sim.set_x(sc["x_after_init"])
+        sim.upload()
+        return sim, t
+
+    def timed_resident(sim, sampler=None):
+        """CONDITION_FRAMES + --warmup untimed frames, then EXACTLY --steps frames between barriers; CUDA events on the library's stream."""
+        sim.step_resident(frames=CONDITION_FRAMES)
+        sim.step_resident(frames=max(args.warmup, 3))
+        barrier()
+        l0 = sim.info()["launches_total"]
+        if sampler:
+            sampler.begin()
+        sim.step_resident(frames=args.steps)
+        if sampler:
+            sampler.end()
+        ms = sim.last_region_ms()
+        l1 = sim.info()["launches_total"]
+        barrier()
+        return ms, l1 - l0
+
+    import ensemble  # whole-job figures: MAX over ranks of the timed region, SUM over ranks of the units
+
+    # ---- resident path: `value` (N > 1: one replica of the scene per GPU, no data-path collective) ------------------------
+    sim, t_setup = build()
+    info0 = sim.info()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    sim.step_resident(frames=args.warmup)
-    barrier()
-    l0 = sim.info()["launches_total"]
-    sampler.begin()
-    sim.step_resident(frames=args.steps)      # the timed region: K frames, CUDA events on the library's stream
-    sampler.end()
-    ms_region = sim.last_region_ms()
-    l1 = sim.info()["launches_total"]
-    barrier()
+    ms_region, launches = timed_resident(sim, sampler)
     clocks = sampler.stop()
-    # second pass with per-phase events (not part of `value`): local / rhs / solve split
+    # per-phase split, same regime (the optimiser reached its steady state in the conditioning frames): CUDA events around
+    # the three phases of every iteration, as many frames as the timed region
     sim.timing(True)
     sim.timing_read(reset=True)
-    sim.step_resident(frames=max(2, args.steps // 2))
+    sim.step_resident(frames=args.steps)
     phases = sim.timing_read(reset=True)
     sim.timing(False)
+    flops = algorithmic_flops_per_tet(sim, sc) if (hyper and rank == 0) else None
 
     # ---- end to end through admmb_step with host buffers: `e2e` ---------------------------------------------------
     sim.download()
-    for _ in range(2):
+    for _ in range(3):
         sim.step()
     barrier()
     t0 = time.perf_counter()
@@ -357,14 +493,33 @@ def main():
     torch.cuda.synchronize()
     sec_e2e = time.perf_counter() - t0
     barrier()
-
-    import ensemble  # whole-job figures: MAX over ranks of the timed region, SUM over ranks of the units
-    ms_region_max, total_iters = ensemble.reduce_job(ms_region, args.steps * ADMM_ITERS)
-    ms_e2e_max, _ = ensemble.reduce_job(sec_e2e * 1e3, args.steps * ADMM_ITERS)
-    if dist_arg is not None:
-        total_iters = args.steps * ADMM_ITERS   # one mesh: the ranks share the same iterations
+    ms_region_max, total_iters = ensemble.reduce_job(ms_region, args.steps * iters_per_frame)
+    ms_e2e_max, _ = ensemble.reduce_job(sec_e2e * 1e3, args.steps * iters_per_frame)
     value = total_iters / (ms_region_max * 1e-3)
     e2e_value = total_iters / (ms_e2e_max * 1e-3)
+    sim.close()
+
+    # ---- N > 1: the same mesh ONCE, partitioned over the ranks (strong scaling) ------------------------------------------
+    partition = None
+    if world > 1 and args.partition != "off" and not args.scene:
+        holder = [admm_b200.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(holder, src=0)
+        psolver = admm_b200.SOLVER_PCG if args.partition == "pcg" else admm_b200.SOLVER_DIRECT
+        psim, pt_setup = build(dist_arg=(rank, world, holder[0]), solver=psolver)
+        pms, planches = timed_resident(psim)
+        psim.timing(True)
+        psim.timing_read(reset=True)
+        psim.step_resident(frames=max(2, args.steps // 2))
+        pph = psim.timing_read(reset=True)
+        psim.timing(False)
+        pms_max, _ = ensemble.reduce_job(pms, 0)
+        pit = max(pph["iters"], 1)
+        partition = {"value": args.steps * iters_per_frame / (pms_max * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": pms_max / args.steps,
+                     "mode": "local step partitioned by elements; " + ("Jacobi-PCG rows partitioned, NCCL all-gather + all-reduce per CG iteration" if args.partition == "pcg"
+                                                                      else "right-hand side all-gathered (ncclAllGather of 3n doubles per ADMM iteration), direct solve replicated on every rank"),
+                     "phases_ms_per_iteration_rank0": {"local": pph["local_ms"] / pit, "rhs_and_allgather": pph["rhs_ms"] / pit, "solve": pph["solve_ms"] / pit},
+                     "gpu_launches_rank0": int(planches), "replica_it_s_per_gpu": value / world}
+        psim.close()
 
     if rank == 0:
         pk = peaks()
@@ -374,59 +529,72 @@ def main():
         solve_ms = phases["solve_ms"] / iters
         local_ms = phases["local_ms"] / iters
         rhs_ms = phases["rhs_ms"] / iters
-        # dominant kernel of the global step: k_solve_level streams the packed factor once forward and once backward
+        phase_sum = local_ms + rhs_ms + solve_ms
+        step_ms = ms_region_max / args.steps / iters_per_frame
+        # global step: k_solve_level streams the packed factor once forward and once backward
         solve_bytes = info0["factor_bytes"] + 9 * nverts * 8 * 3  # factor tiles + b, y, x vectors read/written
         solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
-        # local step: algorithmic bytes per tet-iteration: idx 16 + x gather 96 + B 96 + u r/w 144 + z w 72
-        # + state r/w 64 + weights 24 + P w 96 = 608 B
-        local_bytes = 608.0 * ntets
-        local_gbs = local_bytes / (local_ms * 1e-3) / 1e9 if local_ms > 0 else 0.0
-        # Two kernels carry the step.  k_solve_level (global step) is HBM bound and is the `roofline` object;
-        # k_local_tets_hyper (local step) is the larger share of the time but is FP64-pipe bound, which the
-        # hbm|tensor schema cannot express, so it is reported beside it as `roofline_local`.
-        step_ms = ms_region_max / args.steps / ADMM_ITERS
-        roof = {"bound": "hbm", "kernel": f"k_solve_level_pf ({2 * info0['n_levels']} launches per solve)", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": solve_gbs / hbm_peak, "traffic": SOLVE_DRAM_BYTES_NCU if args.cube == 55 else None, "peak_source": peak_src,
-                "share_of_step": solve_ms / (local_ms + rhs_ms + solve_ms),
-                "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; "
-                        f"{info0['n_levels']} levels; traffic = dram bytes of these launches summed, ncu profiles/r1e_solve.txt (cube N=55 only)"}
-        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        fp64_peak = 148 * 64 * 2 * sm_clock / 1e12   # 64 DFMA lanes per SM per clock (ncu: sm__sass_thread_inst_executed_op_dfma peak)
-        local_tflops = EXEC_FP64_FLOPS_PER_TET_ITER * ntets / (local_ms * 1e-3) / 1e12 if local_ms > 0 else 0.0
-        roof_local = {"bound": "fp64", "kernel": "k_local_tets_hyper<NHModel,5>", "achieved": local_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                      "frac": local_tflops / fp64_peak, "share_of_step": local_ms / (local_ms + rhs_ms + solve_ms),
-                      "fp64_pipe_active_pct_ncu": 57.9, "algorithmic_GBps": local_gbs,
-                      "note": "executed FP64 flops per tet-iteration in steady state (DADD + DMUL + 2 DFMA, ncu profiles/r1e_local.txt: "
-                              f"{EXEC_FP64_FLOPS_PER_TET_ITER}); peak = 148 SMs x 64 DFMA/clk x 2 at the sampled SM clock; the kernel is compiled "
-                              "with -fmad=false to stay bit-exact with the reference, so no multiply-add is fused"}
+        roof_global = {"bound": "hbm", "kernel": f"k_solve_level_pf ({2 * info0['n_levels']} launches per solve)", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": solve_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "share_of_step": solve_ms / phase_sum,
+                       "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; {info0['n_levels']} levels; "
+                               "ncu dram traffic of the same launches: profiles/ (1.03x the algorithmic bytes at N=55)"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_region_max / args.steps, "higher_is_better": True, "scaling": "strong" if dist_arg is not None else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cube N={args.cube} ({ntets} tets, {nverts} nodes) NeoHookean mu=lambda=1e5 max_iterations=5, "
-                                   f"{ADMM_ITERS} ADMM iterations per step (System::step), dt 0.04, x1.3 stretch; solver={args.solver}",
-                       "parallelism": (f"one mesh partitioned over {world} ranks: PCG rows + local step, NCCL all-gather/all-reduce" if dist_arg is not None
-                                       else f"ensemble x{world} (one scene per GPU, no collective)") if world > 1 else "single GPU",
-                       "cg_iterations_per_admm_iteration": (sim.info()["cg_iters_total"] / max(1, sim.info()["elapsed_s"] / sc["dt"] * ADMM_ITERS)) if args.solver == "pcg" else None,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_region_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic" if not args.scene else "shipped scene",
+            "config": {"workload": label + f"; solver={args.solver}",
+                       "conditioning": f"{CONDITION_FRAMES} untimed frames before the --warmup frames on every arm (the reference's line search needs ~20 frames to reach "
+                                       "its steady regime: maxfev evaluations in almost every tet)",
+                       "parallelism": f"ensemble x{world} (one scene per GPU, no collective); the single mesh partitioned over the same GPUs is `partition`" if world > 1 else "single GPU",
                        "l2": "working set (factor %.2f GB + force arrays %.2f GB) exceeds the 126 MB L2, no flush needed" % (
-                           info0["factor_bytes"] / 1e9, 608.0 * ntets / 1e9)},
+                           info0["factor_bytes"] / 1e9, LOCAL_BYTES_PER_TET * ntets / 1e9) if not args.scene else
+                             "small scene: the working set fits the L2 by nature (what the reference's users run); no flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 3 * nverts * 8, "d2h_bytes_per_step": 2 * 3 * nverts * 8,
                     "ms_per_step": ms_e2e_max / args.steps,
                     "note": "admmb_step(iters, m_x, m_v): host x and v in and out every step, buffers page-locked once with "
                             "admmb_register_host_buffer (pinned host memory, as the contract asks)"},
-            "gpu_launches": int(l1 - l0),
+            "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof,
-            "roofline_local": roof_local,
-            "phases_ms_per_iteration": {"local": local_ms, "rhs": rhs_ms, "solve": solve_ms,
-                                        "local_GBps_algorithmic": local_gbs, "solve_GBps": solve_gbs},
+            "phases_ms_per_iteration": {"local": local_ms, "rhs": rhs_ms, "solve": solve_ms, "sum": phase_sum, "step": step_ms,
+                                        "note": "phases: CUDA events around each phase in a second pass of --steps frames in the same (conditioned) regime; "
+                                                "step = ms_per_step / iterations of the timed region itself"},
             "setup": {"seconds": t_setup, "factor_seconds": info0["factor_seconds"], "nnz_L": info0["nnz_L"],
                       "supernodes": info0["n_supernodes"], "levels": info0["n_levels"], "factor_bytes": info0["factor_bytes"]},
         }
+        if hyper:
+            # The dominant kernel is the hyperelastic local step: FP64-pipe bound, not HBM or tensor bound.  Its roofline uses
+            # MEASURED denominators (admmb_probe_fp64 on this device, now) and COUNTED algorithmic flops (this run's tets).
+            fp = admm_b200.probe_fp64(local_rank)
+            peak_fma = 2.0 * fp["dfma_tinst_s"]                       # Tflop/s if every instruction were a fused multiply-add
+            peak_nofma = 0.5 * (fp["dadd_tinst_s"] + fp["dmul_tinst_s"])  # Tflop/s of unfused adds / multiplies: all the bit-exact path may issue
+            alg = flops["flops_per_tet_iteration"] * ntets / (local_ms * 1e-3) / 1e12 if local_ms > 0 else 0.0
+            line["roofline"] = {
+                "bound": "fp64", "kernel": "k_local_tets_hyper<NHModel,5> (1 launch per ADMM iteration)", "achieved": alg, "peak": peak_fma, "unit": "TFLOP/s",
+                "frac": alg / peak_fma, "traffic": None, "share_of_step": local_ms / phase_sum,
+                "peak_source": "admmb_probe_fp64 on this device in this run: independent DFMA chains, 2 flops each (of measured)",
+                "frac_of_unfused_peak": alg / peak_nofma, "unfused_peak": peak_nofma,
+                "algorithmic_flops_per_tet_iteration": flops["flops_per_tet_iteration"], "flop_count": flops,
+                "algorithmic_GBps": LOCAL_BYTES_PER_TET * ntets / (local_ms * 1e-3) / 1e9 if local_ms > 0 else 0.0,
+                "fp64_probe": fp,
+                "note": "achieved = counted algorithmic flops (add / mul / div / sqrt / log = 1 each, host restatement of the kernel body on a sample of this run's "
+                        "tets) x tets / measured kernel time.  The kernel restates x86 arithmetic bit for bit, so no multiply-add may be fused (-fmad=false) and every "
+                        "division / sqrt / log expands into 9-27 FP64 instructions: frac_of_unfused_peak is the fraction of what unfused FP64 issue can deliver; "
+                        "pipe utilisation itself is in profiles/ (ncu)"}
+            line["roofline_global"] = roof_global
+        else:
+            line["roofline"] = roof_global
+        if partition is not None:
+            line["partition"] = partition
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(args.cpu_cube)
+            line["cpu_baseline"] = cpu_baseline_leg(args.cpu_cube) if not args.scene else None
+            if args.scene:
+                from oracle import ref
+                if ref.available():
+                    r = reference_rate(sc, args.steps, max(args.warmup, 10))
+                    line["cpu_baseline"] = {"value": r["it_s"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": f"the whole workload ({label}), {args.steps} frames"}
+        if world == 1 and not args.no_pairs and not args.scene:
+            line["same_config_pairs"] = same_config_pairs(local_rank, [w for w in args.pairs.split(",") if w])
         print(json.dumps(line))
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -95,6 +95,9 @@ int admmb_add_collision(admmb_ctx *ctx, int nshapes, const int *shape_kind, cons
  *   earlier triangles sharing a node with it (its multi-threaded loop races on v); reproduced bit for bit on the device
  *   by walking the dependency wavefronts.  Subsets and wind must be registered before admmb_finalize. */
 int admmb_set_gravity(admmb_ctx *ctx, int id, const double *dir3);
+/* Skip (on = 0) or re-apply (on = 1) a registered explicit force: what erasing / re-inserting an entry of
+ * System::explicit_forces between steps does in the reference (System.cpp:37-39 walks the vector every frame). */
+int admmb_enable_explicit(admmb_ctx *ctx, int id, int on);
 int admmb_add_explicit_subset(admmb_ctx *ctx, int count, const int *idx, const double *dir3);
 int admmb_add_wind(admmb_ctx *ctx, int ntris, const int *tris3, const double *dir3);
 
@@ -117,11 +120,17 @@ int admmb_set_deterministic(admmb_ctx *ctx, int on);
 /* Solver choice and tolerances; call before admmb_finalize.  tol and max_cg_iters apply to PCG only. */
 int admmb_set_solver(admmb_ctx *ctx, int solver, double tol, int max_cg_iters);
 
-/* One mesh partitioned over several GPUs, one process per GPU (PCG solver only; the direct solve does not shard --
- * replicas only).  Rank 0 creates an id with admmb_dist_unique_id (an ncclUniqueId, 128 bytes) and distributes it out
- * of band; every rank then calls admmb_dist_init before admmb_finalize and afterwards makes the SAME calls with the
- * SAME data as in the single-GPU case: setup, x and v are replicated, the local step and the rows of the solve are
- * partitioned, NCCL carries the all-gather of the CG search direction / solution and the dot-product all-reduces. */
+/* One mesh partitioned over several GPUs, one process per GPU.  Rank 0 creates an id with admmb_dist_unique_id (an
+ * ncclUniqueId, 128 bytes) and distributes it out of band; every rank then calls admmb_dist_init before admmb_finalize
+ * and afterwards makes the SAME calls with the SAME data as in the single-GPU case: setup, x and v are replicated and
+ * the local step is partitioned (every rank evaluates the forces that touch its chunk of the nodes).
+ *   ADMMB_SOLVER_DIRECT: the owned rows of the right-hand side are all-gathered (NCCL, 3n doubles per ADMM iteration)
+ *     and every rank runs the prefactored solve redundantly -- sparse triangular solves do not shard -- then
+ *     the ranks' chunks of the solution are all-gathered so that all ranks continue from bit-identical positions.
+ *   ADMMB_SOLVER_PCG: the rows of the solve are partitioned too; NCCL carries the all-gather of the CG search direction /
+ *     solution and the dot-product all-reduces.
+ * admmb_get_state(Z / U / PROX / PROX_ITERS) on a partitioned mesh returns NaN for the forces this rank does not hold
+ * (merge the ranks' exports by taking the non-NaN entries); admmb_set_state ignores them. */
 int admmb_dist_unique_id(char *out128);
 int admmb_dist_init(admmb_ctx *ctx, int rank, int world, const char *id128);
 

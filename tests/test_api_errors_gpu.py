@@ -222,3 +222,67 @@ def test_step_async_with_host_buffers_matches_step():
         sims[0].sync()
         for s in sims:
             s.close()
+
+
+def test_pending_async_step_blocks_calls_that_would_overwrite_its_staging():
+    """admmb_step_async parks the step's results in the context's staging areas until admmb_sync: every call that uses the
+    same areas must refuse to run in between (ADMMB_E_STATE) instead of silently corrupting the pending x / v."""
+    sc = scenes.cube_scene(3, kind=scenes.TET_ARAP, seed=3)
+    sim = admm_b200.System(sc)
+    sim.set_x(sc["x_after_init"])
+    sim.step()
+    ref = admm_b200.System(sc)
+    ref.set_x(sc["x_after_init"])
+    ref.step()
+    ref.step()
+    L, h = sim.L, sim.h
+    sim.step_async()
+    f32 = np.zeros(sim.n3, dtype=np.float32)
+    tmp = np.zeros(sim.n3)
+    assert L.admmb_download_x_f32(h, f32) == -2
+    assert L.admmb_debug_local_step(h, tmp) == -2
+    assert L.admmb_get_state(h, admm_b200.STATE_X, tmp) == -2
+    assert L.admmb_step(h, 1, tmp, tmp.copy()) == -2
+    assert L.admmb_recompute_weights(h) == -2
+    assert b"admmb_sync" in L.admmb_last_error(h)
+    sim.sync()
+    assert np.linalg.norm(sim.m_x - ref.m_x) <= 1e-12 * np.linalg.norm(ref.m_x)
+    assert L.admmb_download_x_f32(h, f32) == 0
+    sim.close()
+    ref.close()
+
+
+def test_failed_refactorisation_makes_the_context_refuse_to_step_until_repaired():
+    sc = scenes.cube_scene(2, kind=scenes.TET_ARAP, seed=3)
+    sim = admm_b200.System(sc)
+    T = sc["batches"][0]["idx"].shape[0]
+    w0 = sim.get_batch_weights(sim.batch_ids[0], T)
+    sim.set_batch_weights(sim.batch_ids[0], np.full(T, np.nan))
+    with pytest.raises(admm_b200.AdmmError):
+        sim.recompute_weights()                   # NaN weights: the factorisation reports a pivot failure
+    x = sim.m_x.copy()
+    assert sim.L.admmb_step(sim.h, 1, x, x.copy()) == -2
+    assert b"unusable" in sim.L.admmb_last_error(sim.h)
+    sim.set_batch_weights(sim.batch_ids[0], w0)
+    sim.recompute_weights()                       # repaired
+    sim.step()
+    assert np.isfinite(sim.m_x).all()
+    sim.close()
+
+
+def test_disabled_explicit_force_is_skipped():
+    sc = scenes.cube_scene(2, kind=scenes.TET_ARAP, stretch=None)
+    a = admm_b200.System(sc, iters=0)
+    b = admm_b200.System(sc, iters=0)
+    assert len(a.gravity_ids) == 1
+    assert a.L.admmb_enable_explicit(a.h, a.gravity_ids[0], 0) == 0
+    assert a.L.admmb_enable_explicit(a.h, 99, 0) == -1
+    a.step()
+    b.step()
+    assert np.array_equal(a.m_v, np.zeros_like(a.m_v))       # no gravity: nothing moves
+    assert np.abs(b.m_v).max() > 0
+    a.L.admmb_enable_explicit(a.h, a.gravity_ids[0], 1)
+    a.step()
+    assert np.array_equal(a.m_v, b.m_v)                      # first frame of gravity from rest, as b's
+    a.close()
+    b.close()

@@ -1,8 +1,13 @@
-"""One mesh partitioned over two GPUs: replicated setup, partitioned local step and PCG rows,
-NCCL all-gather / all-reduce on the data path.  Needs two CUDA devices (gpurun --gpus 2); skipped otherwise.
-Every rank must reproduce the single-GPU PCG result."""
+"""One mesh partitioned over two GPUs.  Needs two CUDA devices (gpurun --gpus 2); skipped otherwise.
+
+* direct solver: the local step is partitioned (every rank evaluates the forces that touch its chunk of the nodes), the owned
+  rows of the right-hand side are all-gathered and every rank solves redundantly.  The owned rows are summed from the same
+  slots in the same order as on one GPU, so with the deterministic solve the partitioned run must reproduce the single-GPU run
+  BIT FOR BIT (positions, and z / u / optimiser state merged from the ranks' exports); with the default (atomic) solve the ranks
+  must still agree with each other bit for bit (their solution chunks are exchanged) and with one GPU to rounding.
+* PCG: partitioned rows, NCCL all-gather / all-reduce per CG iteration; every rank must reproduce the single-GPU PCG result.
+"""
 import multiprocessing as mp
-import os
 
 import numpy as np
 import pytest
@@ -12,50 +17,115 @@ import scenes
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, uid, scene_kw, frames, q):
+def _worker(rank, world, uid, scene_kw, frames, solver, deterministic, q):
     import admm_b200
     sc = scenes.cube_scene(**scene_kw)
-    sim = admm_b200.System(sc, device=rank, solver=admm_b200.SOLVER_PCG, cg_tol=1e-13, dist=(rank, world, uid))
+    sim = admm_b200.System(sc, device=rank, solver=solver, cg_tol=1e-13, dist=(rank, world, uid), deterministic=deterministic)
     sim.set_x(sc["x_after_init"])
     xs = []
     for _ in range(frames):
         sim.step()
         xs.append(sim.m_x.copy())
+    # a few more frames through the resident (CUDA graph) path, which is what bench.py times
+    sim.step_resident(frames=2)
+    sim.download()
+    xs.append(sim.m_x.copy())
     info = sim.info()
+    u, z, st = sim.u, sim.z, sim.prox_state()
     sim.close()
-    q.put((rank, np.array(xs), info["cg_iters_total"]))
+    q.put((rank, np.array(xs), info["cg_iters_total"], u, z, st))
 
 
-@pytest.mark.parametrize("kind,label", [(scenes.TET_ARAP, "arap"), (scenes.TET_NH, "nh")])
-def test_two_rank_partition_matches_single_gpu(kind, label):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+def _single(kw, frames, solver, deterministic):
     import admm_b200
-    kw = dict(N=8, kind=kind, seed=31)
-    frames = 3
     sc = scenes.cube_scene(**kw)
-    ref = admm_b200.System(sc, device=0, solver=admm_b200.SOLVER_PCG, cg_tol=1e-13)
+    ref = admm_b200.System(sc, device=0, solver=solver, cg_tol=1e-13, deterministic=deterministic)
     ref.set_x(sc["x_after_init"])
     xr = []
     for _ in range(frames):
         ref.step()
         xr.append(ref.m_x.copy())
-    xr = np.array(xr)
+    ref.step_resident(frames=2)
+    ref.download()
+    xr.append(ref.m_x.copy())
+    out = np.array(xr), ref.u, ref.z, ref.prox_state()
     ref.close()
+    return out
+
+
+def _two_ranks(kw, frames, solver, deterministic):
+    import admm_b200
     uid = admm_b200.dist_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, uid, kw, frames, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, uid, kw, frames, solver, deterministic, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    return res
+
+
+def _need_two():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+
+
+def _merge(a, b):
+    """Ranks export NaN for the forces they do not hold; forces on the cut are held -- identically -- by both."""
+    both = ~np.isnan(a) & ~np.isnan(b)
+    assert np.array_equal(a[both], b[both])
+    out = np.where(np.isnan(a), b, a)
+    assert not np.isnan(out).any()
+    return out
+
+
+@pytest.mark.parametrize("kind,label", [(scenes.TET_ARAP, "arap"), (scenes.TET_NH, "nh")])
+def test_two_rank_direct_deterministic_is_bit_identical_to_one_gpu(kind, label):
+    _need_two()
+    import admm_b200
+    kw = dict(N=10, kind=kind, seed=31)
+    frames = 3
+    xr, ur, zr, sr = _single(kw, frames, admm_b200.SOLVER_DIRECT, True)
+    res = _two_ranks(kw, frames, admm_b200.SOLVER_DIRECT, True)
+    x0, x1 = res[0][1], res[1][1]
+    assert np.array_equal(x0, x1), "ranks disagree"
+    assert np.array_equal(x0, xr), f"{label}: partitioned run differs from the single-GPU run: {np.abs(x0 - xr).max():.3e}"
+    assert np.array_equal(_merge(res[0][3], res[1][3]), ur)
+    assert np.array_equal(_merge(res[0][4], res[1][4]), zr)
+    if sr.size:
+        assert np.array_equal(_merge(res[0][5], res[1][5]), sr)
+
+
+def test_two_rank_direct_default_solve_ranks_identical():
+    _need_two()
+    import admm_b200
+    kw = dict(N=10, kind=scenes.TET_ARAP, seed=31)
+    frames = 3
+    xr = _single(kw, frames, admm_b200.SOLVER_DIRECT, False)[0]
+    res = _two_ranks(kw, frames, admm_b200.SOLVER_DIRECT, False)
+    x0, x1 = res[0][1], res[1][1]
+    assert np.array_equal(x0, x1), "ranks disagree although their solution chunks are exchanged"
+    err = max(np.linalg.norm(x0[f] - xr[f]) / np.linalg.norm(xr[f]) for f in range(len(xr)))
+    print(f"2-rank direct (atomic solve) vs 1 GPU rel-L2 {err:.2e}")
+    assert err <= 1e-9   # ARAP is reproducible in the reference: north_star's per-iteration gate
+
+
+@pytest.mark.parametrize("kind,label", [(scenes.TET_ARAP, "arap"), (scenes.TET_NH, "nh")])
+def test_two_rank_pcg_matches_single_gpu(kind, label):
+    _need_two()
+    import admm_b200
+    kw = dict(N=8, kind=kind, seed=31)
+    frames = 3
+    xr = _single(kw, frames, admm_b200.SOLVER_PCG, False)[0]
+    res = _two_ranks(kw, frames, admm_b200.SOLVER_PCG, False)
     x0, x1 = res[0][1], res[1][1]
     same = np.array_equal(x0, x1)
-    err = max(np.linalg.norm(x0[f] - xr[f]) / np.linalg.norm(xr[f]) for f in range(frames))
+    err = max(np.linalg.norm(x0[f] - xr[f]) / np.linalg.norm(xr[f]) for f in range(len(xr)))
     print(f"{label}: ranks identical: {same}; 2-rank vs 1-GPU PCG rel-L2 {err:.2e}; CG iterations {res[0][2]}")
     assert same
-    assert err <= (1e-9 if kind == scenes.TET_ARAP else 1e-3)   # NH: the reference algorithm itself is chaotic at 1e-5
+    # NH: the reference algorithm itself amplifies the CG tolerance (1e-13) to ~1e-5 within a few frames (DESIGN 5); ARAP does not
+    assert err <= (1e-9 if kind == scenes.TET_ARAP else 1e-3)

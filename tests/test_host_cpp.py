@@ -132,3 +132,24 @@ def test_cpp_host_layer_matches_c_abi_and_golden(name, tmp_path):
     print(f"{name}: C++ host layer vs C ABI bit-identical: {same}; vs golden x {err:.1e} (gate {tol:.1e})")
     assert err <= tol
     assert max(rel_l2(xs[f], res["x"][f]) for f in range(frames)) <= tol
+
+
+def test_user_defined_explicit_force_keeps_all_explicit_forces_on_the_host(tmp_path):
+    """The host layer runs the reference's own ExplicitForce / WindForce on the device; a user subclass in the list sends
+    EVERY explicit force through its host project() in list order instead (no reordering, no double application).  Wind
+    reads the velocities gravity has just changed, so the order matters: both routes must give the same frames."""
+    binary = _need("host_check")
+    sc = scenes.load_scene(os.path.join(GOLDEN, "cloth6x4.scene.npz"))
+    assert [e["type"] for e in sc["explicit"]] == ["gravity", "wind"]
+    frames = 3
+    txt = str(tmp_path / "scene.txt")
+    write_scene_txt(txt, sc, frames)
+    xs = []
+    for mode in ([], ["userforce"]):
+        out = str(tmp_path / f"x{len(mode)}.bin")
+        r = subprocess.run([binary, txt, out] + mode, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        xs.append(np.fromfile(out, dtype=np.float64).reshape(frames, -1))
+    err = max(rel_l2(xs[1][f], xs[0][f]) for f in range(frames))
+    print(f"device explicit forces vs host explicit forces (user subclass present): rel-L2 {err:.1e}")
+    assert err <= 1e-12   # the solve accumulates with atomics: identical up to its last bits

@@ -15,13 +15,13 @@ print(s.info()["n_levels"])
 PY
 )
 PER=$((2 + 2 * NL))                    # local + rhs + 2 x levels (ADMMB_NO_GRAPH=1: one launch per kernel)
-SKIP=$((20 * (10 * PER + 2) + 4))      # 20 warm-up frames (+ frame begin / end), upload permutes
+SKIP=$((23 * (10 * PER + 2) + 4))      # 20 conditioning + 3 warm-up frames (+ frame begin / end), upload permutes
 echo "levels $NL, launches per iteration $PER, skipping $SKIP" > $OUT/profile_${TAG}.log
 ADMMB_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__grid_size --clock-control none \
-    -s $SKIP -c $((3 * PER + 2)) --csv --log-file $OUT/launches_${TAG}.csv python bench.py --cube 55 --steps 2 --warmup 20 --no-cpu-baseline >> $OUT/profile_${TAG}.log 2>&1
+    -s $SKIP -c $((3 * PER + 2)) --csv --log-file $OUT/launches_${TAG}.csv python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
 [ -n "$LIST_ONLY" ] && { tail -3 $OUT/profile_${TAG}.log; exit 0; }
-ADMMB_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:k_local_tets_hyper -s 205 -c 1 -f -o $OUT/prof_local_${TAG} \
-    python bench.py --cube 55 --steps 2 --warmup 20 --no-cpu-baseline >> $OUT/profile_${TAG}.log 2>&1
-ADMMB_NO_GRAPH=1 ncu --set full --clock-control none -k regex:k_solve_level -s $((20 * 10 * 2 * NL)) -c $((2 * NL)) -f -o $OUT/prof_solve_${TAG} \
-    python bench.py --cube 55 --steps 2 --warmup 20 --no-cpu-baseline >> $OUT/profile_${TAG}.log 2>&1
+ADMMB_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:k_local_tets_hyper -s 235 -c 1 -f -o $OUT/prof_local_${TAG} \
+    python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
+ADMMB_NO_GRAPH=1 ncu --set full --clock-control none -k regex:k_solve_level -s $((23 * 10 * 2 * NL)) -c $((2 * NL)) -f -o $OUT/prof_solve_${TAG} \
+    python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
 tail -3 $OUT/profile_${TAG}.log

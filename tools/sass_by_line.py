@@ -19,14 +19,25 @@ h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[h]
 iS, iE, iN = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 base = int(rows[h + 1][0], 16)
-REGIONS = [  # elastic_math.h line ranges
-    ("svd3", 52, 230), ("glibc_log", 231, 322), ("nh/stvk eval", 323, 442), ("mt_cstep", 443, 521),
-    ("mt_linesearch", 522, 617), ("lbfgs", 618, 732), ("other math", 733, 99999)]
+# regions = the functions of elastic_math.h / local_bodies.h, found from the source text (pass the directory with --src DIR)
+import os
+SRC = sys.argv[sys.argv.index("--src") + 1] if "--src" in sys.argv else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "admm-elastic-sca_b200", "csrc")
+def functions(path):
+    out = []
+    if not os.path.exists(path): return out
+    for i, l in enumerate(open(path).read().splitlines(), 1):
+        m = re.match(r'^(?:\s{0,1})(?:static\s+)?(?:ADMMB_\w+|__device__ __forceinline__)\s+[\w:<>\s\*&]*?\b(\w+)\s*\(', l)
+        if m and not l.startswith("\t\t"): out.append((i, m.group(1)))
+    return out
+FUNCS = {f: functions(os.path.join(SRC, f)) for f in ("elastic_math.h", "local_bodies.h")}
 def region(f, ln):
-    if f == "elastic_math.h":
-        for n, a, b in REGIONS:
-            if a <= ln <= b: return n
-    return f
+    fs = FUNCS.get(f)
+    if not fs: return f
+    name = f
+    for start, nm in fs:
+        if start <= ln: name = nm
+        else: break
+    return name
 ex = collections.Counter(); sm = collections.Counter(); fp = collections.Counter(); perline = collections.Counter(); pls = collections.Counter()
 tot = tots = 0
 for r in rows[h + 1:]:
