@@ -544,42 +544,49 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 		ctx->launches += ctx->iter_graph_launches * admm_iters;
 		return ADMMB_OK;
 	}
-	// Timed mode with the direct solver: the three phases are captured as three small graphs so that the per-phase
-	// event timings see the same launch behaviour as the production path (one graph per iteration).
-	if (timed && !dump && ctx->use_graph && ctx->solver == ADMMB_SOLVER_DIRECT) {
-		if (!(ctx->phase_graph_exec[0] && ctx->phase_graph_exec[1] && ctx->phase_graph_exec[2])) {
+	// Timed mode with the direct solver: the frame's iterations are captured ONCE into a graph whose kernel nodes are the
+	// production ones and whose phase boundaries are event-record nodes (cudaEventRecordExternal), so that the per-phase
+	// timings see the launch behaviour of the production path -- no extra graph launches or host work between phases.
+	if (timed && !dump && ctx->use_graph && ctx->solver == ADMMB_SOLVER_DIRECT && admm_iters > 0) {
+		Timing &T = ctx->timing;
+		const size_t first = T.used; // events [first, first + 4 * admm_iters) belong to this frame's iterations
+		if (!ctx->phase_graph_exec[0] || ctx->timed_graph_iters != admm_iters || ctx->timed_graph_first != first) {
+			if (ctx->phase_graph_exec[0]) { cudaGraphExecDestroy(ctx->phase_graph_exec[0]); ctx->phase_graph_exec[0] = nullptr; }
+			while (T.ev.size() < first + 4 * (size_t)admm_iters) { cudaEvent_t e; cudaEventCreate(&e); T.ev.push_back(e); }
 			const long before = ctx->launches;
-			for (int ph = 0; ph < 3; ++ph) {
-				cudaGraph_t g = nullptr;
-				ADMMB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-				int rc = ADMMB_OK;
-				if (ph == 0) { for (Batch &b : ctx->batches) if ((rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2))) break; }
-				else if (ph == 1) rc = rhs_phase(ctx);
-				else rc = solve_phase(ctx);
-				cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-				if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&ctx->phase_graph_exec[ph], g, 0);
-				if (g) cudaGraphDestroy(g);
-				if (rc || e != cudaSuccess) {
-					// no half-built set of phase graphs may survive: the next timed step would launch a null graph
-					drop_iteration_graph(ctx);
-					ctx->launches = before;
-					cudaGetLastError();
-					if (ctx->dist_world > 1) { ctx->use_graph = false; return run_iterations(ctx, admm_iters, dump); }
-					if (rc) return rc;
-					ADMMB_CUDA(ctx, e);
-				}
+			cudaGraph_t g = nullptr;
+			ADMMB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+			int rc = ADMMB_OK;
+			cudaError_t e = cudaSuccess;
+			size_t k = first;
+			for (int it = 0; it < admm_iters && !rc && e == cudaSuccess; ++it) {
+				e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
+				for (Batch &b : ctx->batches) if (!rc) rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
+				if (e == cudaSuccess) e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
+				if (!rc) rc = rhs_phase(ctx);
+				if (e == cudaSuccess) e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
+				if (!rc) rc = solve_phase(ctx);
+				if (e == cudaSuccess) e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
 			}
-			ctx->iter_graph_launches = ctx->launches - before;
+			cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &g);
+			if (e == cudaSuccess) e = e2;
+			if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&ctx->phase_graph_exec[0], g, 0);
+			if (g) cudaGraphDestroy(g);
+			ctx->timed_graph_launches = ctx->launches - before;
 			ctx->launches = before;
-		}
-		for (int it = 0; it < admm_iters; ++it) {
-			next_event(ctx);
-			for (int ph = 0; ph < 3; ++ph) {
-				ADMMB_CUDA(ctx, cudaGraphLaunch(ctx->phase_graph_exec[ph], ctx->stream));
-				next_event(ctx);
+			if (rc || e != cudaSuccess) {
+				drop_iteration_graph(ctx); // nothing half-built may survive
+				cudaGetLastError();
+				if (ctx->dist_world > 1) { ctx->use_graph = false; return run_iterations(ctx, admm_iters, dump); }
+				if (rc) return rc;
+				ADMMB_CUDA(ctx, e);
 			}
+			ctx->timed_graph_iters = admm_iters;
+			ctx->timed_graph_first = first;
 		}
-		ctx->launches += ctx->iter_graph_launches * admm_iters;
+		ADMMB_CUDA(ctx, cudaGraphLaunch(ctx->phase_graph_exec[0], ctx->stream));
+		T.used = first + 4 * (size_t)admm_iters;
+		ctx->launches += ctx->timed_graph_launches;
 		return ADMMB_OK;
 	}
 	for (int it = 0; it < admm_iters; ++it) {

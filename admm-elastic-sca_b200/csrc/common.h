@@ -166,7 +166,10 @@ struct admmb_ctx {
 	bool use_graph = true;
 	cudaGraph_t iter_graph = nullptr;          // one captured ADMM iteration (direct solver)
 	cudaGraphExec_t iter_graph_exec = nullptr;
-	cudaGraphExec_t phase_graph_exec[3] = { nullptr, nullptr, nullptr }; // timed mode: local / rhs / solve
+	cudaGraphExec_t phase_graph_exec[3] = { nullptr, nullptr, nullptr }; // [0]: timed mode, one frame's iterations with event-record nodes at the phase boundaries
+	int timed_graph_iters = 0;       // iterations captured in phase_graph_exec[0]
+	size_t timed_graph_first = 0;    // first event of the pool its record nodes use
+	long timed_graph_launches = 0;
 	long iter_graph_launches = 0;
 	cudaEvent_t ev_region[2] = { nullptr, nullptr }; // around the last admmb_step_resident call
 	double last_region_ms = 0.0;

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(256) k_fastmath_selftest(unsigned long long se
 		const double b = operand(s, ca), c = operand(s, (ca + 1) % 5);
 		if ((i & 15) == 0) a = y;                       // equal operands
 		if ((i & 15) == 1) a = y * 3.0;
+		if ((i & 15) == 2) a = 0.0;                     // exact zeros of both signs over every class of denominator
+		if ((i & 15) == 3) a = -0.0;
 		{
 			bool bad = false;
 			double q = div_by(a, recip_of(y), bad);

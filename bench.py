@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--ref-cube", type=int, default=30, help="cube resolution of the reference arm's bounded sample")
     ap.add_argument("--cpu-cube", type=int, default=20, help="cube resolution of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart / cudaProfilerStop: `ncu --profile-from-start off` then only sees (and only "
+                         "serialises) the kernels of the timed region, so the conditioning frames run at full speed")
     ap.add_argument("--no-pairs", action="store_true", help="skip the same-config reference / b200 pairs (shipped scenes, cube N=30)")
     ap.add_argument("--pairs", default=",".join(PAIR_WORKLOADS), help="comma-separated workloads of the same-config pairs")
     ap.add_argument("--ensemble", type=int, default=0,
@@ -456,7 +459,11 @@ def main():
         l0 = sim.info()["launches_total"]
         if sampler:
             sampler.begin()
+        if args.profile_region:
+            torch.cuda.cudart().cudaProfilerStart()
         sim.step_resident(frames=args.steps)
+        if args.profile_region:
+            torch.cuda.cudart().cudaProfilerStop()
         if sampler:
             sampler.end()
         ms = sim.last_region_ms()

@@ -1,27 +1,20 @@
 #!/bin/bash
-# ncu passes for profiles/: launch list of 3 steady-state ADMM iterations + full captures of the two hot kernels.
-# usage (on the GPU box): bash tools/profile_round.sh r1d
-TAG=${1:-rX}
+# ncu passes for profiles/: launch list of ONE steady-state frame (10 ADMM iterations) + full captures of the two hot kernels.
+# usage (on the GPU box): bash tools/profile_round.sh r2b [extra bench.py flags]
+# bench.py --profile-region brackets its timed region with cudaProfilerStart/Stop and ncu runs with --profile-from-start off,
+# so the 25 conditioning / warm-up frames run at full speed and only the profiled frame is serialised and replayed.
+TAG=${1:-rX}; shift
 export ADMMB_HOST_FACTOR=1   # keep cuSOLVER / cuBLAS setup kernels out of the launch numbering (the factor is the same)
 OUT=gpurun_out
 mkdir -p $OUT
-NL=$(python - <<'PY'
-import sys, os
-sys.path.insert(0, "admm-elastic-sca_b200/pyhost")
-import admm_b200, scenes
-sc = scenes.cube_scene(55)
-s = admm_b200.System(sc)
-print(s.info()["n_levels"])
-PY
-)
-PER=$((2 + 2 * NL))                    # local + rhs + 2 x levels (ADMMB_NO_GRAPH=1: one launch per kernel)
-SKIP=$((23 * (10 * PER + 2) + 4))      # 20 conditioning + 3 warm-up frames (+ frame begin / end), upload permutes
-echo "levels $NL, launches per iteration $PER, skipping $SKIP" > $OUT/profile_${TAG}.log
-ADMMB_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__grid_size --clock-control none \
-    -s $SKIP -c $((3 * PER + 2)) --csv --log-file $OUT/launches_${TAG}.csv python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
+B="python bench.py --cube 55 --steps 1 --warmup 5 --no-cpu-baseline --no-pairs --profile-region $*"
+echo "bench command: $B" > $OUT/profile_${TAG}.log
+ADMMB_NO_GRAPH=1 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__grid_size --clock-control none \
+    --csv --log-file $OUT/launches_${TAG}.csv $B >> $OUT/profile_${TAG}.log 2>&1
 [ -n "$LIST_ONLY" ] && { tail -3 $OUT/profile_${TAG}.log; exit 0; }
-ADMMB_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:k_local_tets_hyper -s 235 -c 1 -f -o $OUT/prof_local_${TAG} \
-    python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
-ADMMB_NO_GRAPH=1 ncu --set full --clock-control none -k regex:k_solve_level -s $((23 * 10 * 2 * NL)) -c $((2 * NL)) -f -o $OUT/prof_solve_${TAG} \
-    python bench.py --cube 55 --steps 2 --warmup 3 --no-cpu-baseline --no-pairs >> $OUT/profile_${TAG}.log 2>&1
+ADMMB_NO_GRAPH=1 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:k_local_tets_hyper -s 4 -c 1 -f -o $OUT/prof_local_${TAG} \
+    $B >> $OUT/profile_${TAG}.log 2>&1
+[ -n "$LOCAL_ONLY" ] && { tail -3 $OUT/profile_${TAG}.log; exit 0; }
+ADMMB_NO_GRAPH=1 ncu --profile-from-start off --set full --clock-control none -k regex:k_solve_level -s 104 -c 26 -f -o $OUT/prof_solve_${TAG} \
+    $B >> $OUT/profile_${TAG}.log 2>&1
 tail -3 $OUT/profile_${TAG}.log
