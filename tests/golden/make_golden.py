@@ -57,8 +57,9 @@ def main():
               f"self-sensitivity x_it {res['sens_x_it']:.1e} z_it {res['sens_z_it']:.1e} u_it {res['sens_u_it']:.1e} v {res['sens_v']:.1e}")
 
 
-def shipped():
-    """The reference's four shipped scenes, loaded by the reference's own scene layer (oracle/_ref/scene_export)."""
+def shipped(only=None, export=True):
+    """The reference's four shipped scenes, loaded by the reference's own scene layer (oracle/_ref/scene_export), and
+    their material variants (scenarios.VARIANTS).  only = names to (re)generate."""
     import subprocess
     import tempfile
     from scenarios import SHIPPED, SHIPPED_FRAMES, build_shipped, parse_exported_scene
@@ -67,11 +68,13 @@ def shipped():
         print("oracle/_ref/scene_export not built (make -C oracle scene_export): skipping the shipped scenes")
         return
     tmp = tempfile.mkdtemp()
-    for name in SHIPPED:
+    for name in (SHIPPED if export else ()):
         txt = os.path.join(tmp, name + ".txt")
         subprocess.run([exe, name, txt], check=True, stdout=subprocess.DEVNULL)
         scenes.save_scene(os.path.join(HERE, f"shipped_{name}.scene.npz"), parse_exported_scene(txt, name))
     for name, sc in build_shipped(HERE).items():
+        if only and name not in only:
+            continue
         ad = RefAdapter(sc["scene"])
         res = run_scenario(ad, sc, dump=True)
         ad.close()
@@ -82,7 +85,35 @@ def shipped():
               f"self-sensitivity x_it {out['sens_x_it']:.1e} x {out['sens_x']:.1e}")
 
 
+def long_runs():
+    """100-frame reference trajectories of the reproducible scenes (every 10th frame kept) + the reference's own sensitivity
+    over the same horizon (4 perturbation patterns: each is a 100-frame reference run)."""
+    from scenarios import build_long
+    for name, sc in build_long(HERE).items():
+        ad = RefAdapter(sc["scene"])
+        res = run_scenario(ad, sc, dump=False)
+        ad.close()
+        keep = list(range(9, sc["frames"], 10))
+        sens = 0.0
+        for seed in SENS_SEEDS[:4]:
+            ad = RefAdapter(sc["scene"])
+            per = run_scenario(ad, sc, dump=False, perturb=1e-15, seed=seed)
+            ad.close()
+            sens = max(sens, max(float(np.linalg.norm(per["x"][f] - res["x"][f]) / np.linalg.norm(res["x"][f])) for f in keep))
+        np.savez_compressed(os.path.join(HERE, f"long_{name}.ref.npz"), x=res["x"][keep], frames=np.array(keep), sens_x=np.float64(sens))
+        print(f"long {name:26s} frames={sc['frames']} kept={len(keep)} self-sensitivity x {sens:.1e}")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] != "shipped":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "all":
         main()
-    shipped()
+        shipped()
+        long_runs()
+    elif what == "shipped":
+        shipped()
+    elif what == "variants":     # only the material variants: the scene fixtures of the four shipped scenes stay as they are
+        from scenarios import VARIANTS
+        shipped(only=set(VARIANTS), export=False)
+    elif what == "long":
+        long_runs()

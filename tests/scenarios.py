@@ -357,8 +357,32 @@ def _poordillo_events(sc):
 SHIPPED_FRAMES = dict(bunnyexpand=12, windyflag=8, poordillo=26, plinkopony=20)  # windyflag: the explicit wind amplifies rounding noise ~3x per frame (5.8e-10 after 12 frames)
 
 
-def build_shipped(golden_dir):
-    """The four shipped scenes as exported by the reference's scene layer (tests/golden/shipped_*.scene.npz)."""
+# BASELINE.json configs 1 and 3 name material VARIANTS of two shipped scenes ("poordillo ... ARAP and StVK variants",
+# "bunnyexpand ... NeoHookean"; SURVEY 8d: "run both"): the same meshes, anchors and events with the tet force swapped the
+# way editing the `type` attribute of the scene XML does (ForceBuilder.cpp:276-446: LinearTetStrain stiffness, StVKTet /
+# NeoHookeanTet mu, lambda, max_iterations).
+VARIANTS = {
+    "poordillo_arap": ("poordillo", dict(kind=TET_ARAP, p0=1e5, p1=0.0, p2=0.0, maxit=0)),
+    "poordillo_stvk": ("poordillo", dict(kind=TET_STVK)),
+    "bunnyexpand_nh": ("bunnyexpand", dict(kind=TET_NH)),
+}
+
+
+def shipped_variant(sc, change):
+    """Copy of a shipped scene with every tet batch's material replaced (mu / lambda / max_iterations kept unless given)."""
+    out = dict(sc)
+    out["batches"] = []
+    for b in sc["batches"]:
+        b = dict(b)
+        if b["type"] == "tets":
+            b.update(change)
+        out["batches"].append(b)
+    return out
+
+
+def build_shipped(golden_dir, variants=True):
+    """The four shipped scenes as exported by the reference's scene layer (tests/golden/shipped_*.scene.npz), plus the
+    material variants BASELINE.json names."""
     import os
     S = {}
     for name in SHIPPED:
@@ -369,4 +393,30 @@ def build_shipped(golden_dir):
         S[name] = dict(scene=sc, frames=SHIPPED_FRAMES[name])
         if name == "poordillo":
             S[name]["events"] = _poordillo_events(sc)
+    if variants:
+        for vname, (base, change) in VARIANTS.items():
+            if base not in S:
+                continue
+            sc = shipped_variant(S[base]["scene"], change)
+            sc["name"] = vname
+            S[vname] = dict(scene=sc, frames=SHIPPED_FRAMES[base])
+            if base == "poordillo":
+                S[vname]["events"] = _poordillo_events(sc)
     return S
+
+
+# 100-frame trajectories (north_star: "trajectories over 100 frames within 1e-6 for collision-free scenes"): scenes whose
+# reference run is reproducible over that horizon.  No user interaction; every 10th frame is kept in the golden file.
+def build_long(golden_dir):
+    S = build_shipped(golden_dir)
+    L = {}
+    if "poordillo_arap" in S:
+        L["poordillo_arap_100"] = dict(scene=S["poordillo_arap"]["scene"], frames=100)
+    if "plinkopony" in S:   # the pony without its pegs: collision-free ARAP under gravity
+        sc = dict(S["plinkopony"]["scene"])
+        sc["batches"] = [b for b in sc["batches"] if b["type"] != "collision"]
+        sc["name"] = "plinkopony_nocontact"
+        L["plinkopony_nocontact_100"] = dict(scene=sc, frames=100)
+    if "windyflag" in S:
+        L["windyflag_100"] = dict(scene=S["windyflag"]["scene"], frames=100)
+    return L

@@ -40,3 +40,21 @@ def test_reference_scene_layer_runs_on_the_gpu_solver(name, tmp_path):
     print(f"{name}: {r.stdout.strip().splitlines()[-1]}; x vs the reference's golden trajectory {err:.1e} (gate {tol:.1e})")
     assert np.isfinite(xs).all()
     assert err <= tol
+    if tol > 1e-2 or name == "windyflag":
+        # Where the reference itself is chaotic the gate above is loose (bunnyexpand: vacuous).  The sharp statement is that
+        # the reference's scene layer on top of the host layer feeds the solver EXACTLY what the exported fixture feeds it
+        # through the C ABI: with the bit-reproducible solve on both sides the two trajectories must be identical in every
+        # bit, and the fixture-driven run is the one the teacher-forced tests pin to the reference (tests/test_shipped_scenes_gpu.py).
+        from scenarios import DevAdapter, build_shipped, run_scenario
+        sc = build_shipped(GOLDEN, variants=False)[name]
+        env = dict(os.environ, ADMMB_DETERMINISTIC="1")
+        out2 = str(tmp_path / "x_det.bin")
+        r2 = subprocess.run([runner, name, xml, str(frames), out2], capture_output=True, text=True, timeout=600, env=env)
+        assert r2.returncode == 0, r2.stdout + r2.stderr
+        xd = np.fromfile(out2, dtype=np.float64).reshape(frames, -1)
+        ad = DevAdapter(sc["scene"], deterministic=True)
+        res = run_scenario(ad, sc, dump=False)
+        ad.close()
+        same = np.array_equal(xd, res["x"])
+        print(f"{name}: scene layer + host layer vs fixture through the C ABI, deterministic solve: bit-identical = {same}")
+        assert same

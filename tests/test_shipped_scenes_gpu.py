@@ -1,4 +1,5 @@
-"""The reference's four shipped scenes (BASELINE.json configs[0..3]: bunnyexpand, windyflag, poordillo, plinkopony),
+"""The reference's four shipped scenes (BASELINE.json configs[0..3]: bunnyexpand, windyflag, poordillo, plinkopony) and the
+material variants BASELINE.json names (poordillo ARAP / StVK, bunnyexpand NeoHookean: scenarios.VARIANTS),
 loaded by the reference's OWN scene layer (SimContext + ForceBuilder + mclscene, oracle/scene_export.cpp) with the GUI
 samples' setup() restated headlessly, exported as fixtures (tests/golden/shipped_*.scene.npz) and run on the device.
 
@@ -21,6 +22,24 @@ pytestmark = pytest.mark.gpu
 SHIP = build_shipped(GOLDEN)
 
 
+def _forced_first_frame(sc, gold):
+    ad = DevAdapter(sc["scene"])
+    sim = ad.sim
+    ev = sc.get("events")
+    if ev is not None:
+        ev(0, ad)
+    xi = gold["x_it"][0]
+    K = xi.shape[0]
+    worst = 0.0
+    for k in range(K):
+        sim.debug_local_step(xi[k])
+        sim.debug_global_step(xi[0])        # x_it[0] is x_bar = x + dt v of the frame (the first iterate)
+        x_next = xi[k + 1] if k + 1 < K else gold["x"][0]
+        worst = max(worst, rel_l2(sim.x_iter, x_next))
+    ad.close()
+    return worst
+
+
 @pytest.mark.parametrize("name", list(SHIP))
 def test_shipped_scene_free_running(name):
     gold = np.load(os.path.join(GOLDEN, f"shipped_{name}.ref.npz"))
@@ -36,8 +55,17 @@ def test_shipped_scene_free_running(name):
     print(f"shipped {name}: {F} frames, max rel-L2 of x {err:.2e}; reference self-sensitivity {sens:.1e}; "
           f"{'gate 1e-9' if reproducible else 'chaotic in the reference itself, gate 30 x sensitivity'}")
     assert np.all(np.isfinite(res["x"]))
-    if tol < 0.5:
+    if tol < 1e-2:
         assert err <= tol
+    else:
+        # The reference run is chaotic (a 1e-15 perturbation of ITS OWN input moves its trajectory by `sens`): a free-running
+        # comparison says nothing, so the committed reference iterates of frame 0 are replayed instead -- x entering every
+        # ADMM iteration is the reference's, u and the optimiser state are carried by the device -- and x leaving each
+        # iteration must match the reference's to the per-iteration gate.  (The live teacher-forced test below additionally
+        # checks z, u and the optimiser state bit for bit when the reference library travelled with the snapshot.)
+        worst = _forced_first_frame(sc, gold)
+        print(f"shipped {name}: frame 0 replayed from the committed reference iterates: worst rel-L2 of x per iteration {worst:.2e}")
+        assert worst <= TOL_ITER
 
 
 @pytest.mark.parametrize("name", list(SHIP))
@@ -45,7 +73,7 @@ def test_shipped_scene_teacher_forced_live(name):
     if not have_ref():
         pytest.skip("oracle/_ref/libadmm_ref.so not present on this box")
     sc = dict(SHIP[name])
-    sc["frames"] = min(sc["frames"], 6 if name != "poordillo" else 22)   # poordillo: include the release at frame 20
+    sc["frames"] = min(sc["frames"], 6 if not name.startswith("poordillo") else (22 if name == "poordillo" else 8))   # poordillo: include the release at frame 20
     ra = RefAdapter(sc["scene"])
     gold = run_scenario(ra, sc, dump=True)
     ra.close()
