@@ -50,11 +50,12 @@ struct DirectSolver {
 	DevBuf<int> d_phase_first, d_phase_count;
 	DevBuf<int> d_err;
 	int n_phases = 0, grid = 0;
-	int mode = 3;   // 3 (default) = launch per level, factor columns requested before the vector gather; 0 = launch per level, gather first;
+	int mode = 4;   // 4 (default) = launch per level, tile by bulk-async copy, programmatic dependent launch between levels; 5 = the bulk-copy ring kernel per level + PDL; 3 = launch per level, factor columns requested before the vector gather; 0 = launch per level, gather first;
 	                // 1 = persistent bulk-async kernel; 2 = per level with programmatic dependent launch (1, 2: measured slower, kept selectable)
 	int unroll = 16; // loads in flight per thread of the per-level kernel (ADMMB_SOLVE_UNROLL = 8 | 16 | 32)
 	int slots = 0;   // resident CTAs of the per-level kernel on the whole device
 	int split = 0;   // ADMMB_SOLVE_SPLIT: 0 = choose per level, else log2 of the forced column split + 1
+	bool no_pdl = false; // ADMMB_SOLVE_NO_PDL=1: mode 4 without programmatic dependent launch (A/B)
 	// bit-reproducible variant (ctx->deterministic): tiles store their partial sums, a second kernel per level adds them
 	// to the vectors in a fixed order (no floating-point atomics)
 	bool det = false;
@@ -370,6 +371,84 @@ __device__ __forceinline__ double load_rhs_elem(const SolveTile &t, const int *_
 	return __ldcg(vecs[(t.flags >> TF_IN_SHIFT) & 3] + 3 * (size_t)gi + k);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Launch per level, tile by bulk-async copy, levels chained by programmatic dependent launch (ADMMB_SOLVE_MODE=4).
+//
+// A level of the 1 M-tet cube is 1 200 ... 5 100 tiles of 32 KB: about one wave of CTAs, so a level lasts as long as ONE
+// CTA's chain of dependent memory round trips (descriptor -> index -> vector gather -> four rounds of factor loads ->
+// atomics, profiles/r2a_solve.txt: 11-27 us per level at 17-60 % of the DRAM bandwidth).  Here one thread of the CTA
+// issues a single cp.async.bulk (UBLKCP) for the whole tile into shared memory -- one round trip, no registers held,
+// completion on an mbarrier -- while the other threads gather the right-hand-side slice; and because the factor does
+// not depend on the vectors, the copy is issued BEFORE griddepcontrol.wait: with programmatic dependent launch the CTAs
+// of level p + 1 start as soon as every CTA of level p is resident, so their tiles stream in during the tail of level p
+// instead of after it.  256 threads multiply the tile from shared memory (4 column groups x 64 rows).
+// ---------------------------------------------------------------------------------------------------------
+#define LT_THREADS 256
+#define LT_GROUPS (LT_THREADS / TILE_R)
+#define LT_SMEM (PS_TILE_BYTES + TILE_C * 3 * 8 + LT_GROUPS * TILE_R * 3 * 8 + 16)
+
+__global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
+                                                                const int *__restrict__ pool, double *vb, double *vy, double *vx) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	double *tile = reinterpret_cast<double *>(smem_raw);                   // 64 x 64, column-major, ld = nrows
+	double *sv = tile + TILE_R * TILE_C;                                    // TILE_C x 3
+	double *part = sv + TILE_C * 3;                                         // LT_GROUPS x 64 x 3 partial sums
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(part + LT_GROUPS * TILE_R * 3);
+	const int tid = threadIdx.x;
+	const SolveTile t = tiles[blockIdx.x];
+	if (tid == 0) {
+		mbar_init(full, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		const unsigned bytes = ((unsigned)(t.nrows * t.ncols * 8) + 15u) & ~15u;
+		mbar_expect_tx(full, bytes);
+		bulk_g2s(tile, data + t.off, bytes, full);
+	}
+	// the next level may start (and fetch ITS tiles) once every CTA of this level has got this far
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	double *vecs[3] = { vb, vy, vx };
+	// index lists do not depend on the previous level
+	int gi = 0;
+	const int c_in = tid / 3, k_in = tid - 3 * c_in;
+	if (tid < 3 * t.ncols) gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c_in] : t.in_idx + c_in;
+	int go = 0;
+	if (tid < 3 * t.nrows) { const int r = tid / 3; go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r; }
+	// the vectors do: wait until the previous level has completed and its sums are visible
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	if (tid < 3 * TILE_C) sv[tid] = (tid < 3 * t.ncols) ? __ldcg(vecs[(t.flags >> TF_IN_SHIFT) & 3] + 3 * (size_t)gi + k_in) : 0.0;
+	__syncthreads(); // sv complete; the mbarrier initialisation is visible to every thread
+	mbar_wait(full, 0u);
+	{
+		const int row = tid & (TILE_R - 1), grp = tid / TILE_R;
+		const double *M = tile + row;
+		const int ld = t.nrows;
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+		if (row < t.nrows) {
+#pragma unroll 4
+			for (int c = grp; c < t.ncols; c += LT_GROUPS) {
+				const double m = M[c * ld];
+				a0 += m * sv[3 * c + 0];
+				a1 += m * sv[3 * c + 1];
+				a2 += m * sv[3 * c + 2];
+			}
+		}
+		part[(grp * TILE_R + row) * 3 + 0] = a0;
+		part[(grp * TILE_R + row) * 3 + 1] = a1;
+		part[(grp * TILE_R + row) * 3 + 2] = a2;
+	}
+	__syncthreads();
+	if (tid < 3 * t.nrows) {
+		const int r = tid / 3, k = tid - 3 * r;
+		double a = (part[(0 * TILE_R + r) * 3 + k] + part[(1 * TILE_R + r) * 3 + k]) + (part[(2 * TILE_R + r) * 3 + k] + part[(3 * TILE_R + r) * 3 + k]);
+		if (t.flags & TF_NEG) a = -a;
+		red_add(vecs[(t.flags >> TF_OUT_SHIFT) & 3] + 3 * (size_t)go + k, a);
+	}
+}
+
+// PDL = true: launched once PER LEVEL (n_phases = 1, no grid barrier) with programmatic dependent launch between the
+// levels (ADMMB_SOLVE_MODE=5): the ring keeps the factor streaming inside a level -- no bubble between "waves" of
+// one-tile CTAs -- and the first PS_STAGES tiles of a CTA are requested before griddepcontrol.wait, i.e. during the tail
+// of the previous level.
+template <bool PDL>
 __global__ void __launch_bounds__(PS_THREADS) k_solve_persistent(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
                                                                  const int *__restrict__ pool, const int *__restrict__ pfirst,
                                                                  const int *__restrict__ pcount, int n_phases, double *vb, double *vy,
@@ -401,6 +480,10 @@ __global__ void __launch_bounds__(PS_THREADS) k_solve_persistent(const SolveTile
 			bulk_g2s(stage + (size_t)i * (TILE_R * TILE_C), data + t.off, bytes, &full[i]);
 			cursor_next(prod, pcount, n_phases, cta, grid);
 		}
+	}
+	if (PDL) {
+		asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+		asm volatile("griddepcontrol.wait;" ::: "memory"); // the vectors of the previous level are complete and visible
 	}
 	int consumed = 0, svbuf = 0;
 	for (int phase = 0; phase < n_phases; ++phase) {
@@ -692,15 +775,24 @@ int direct_setup(admmb_ctx *ctx) {
 		// y plus the per-phase barrier counters live in one allocation so that one memset clears both
 		ADMMB_CUDA(ctx, S.d_y.alloc(3 * (size_t)ctx->n + (size_t)(S.n_phases + 2) / 2 + 2));
 		const int smem = PS_SMEM;
-		ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_solve_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_solve_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 		int occ = 0, sms = 0;
-		ADMMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_persistent, PS_THREADS, smem));
+		ADMMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_persistent<false>, PS_THREADS, smem));
 		ADMMB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
 		S.grid = sms * (occ < 1 ? 1 : occ);
 		{
 			const char *e = getenv("ADMMB_SOLVE_MODE");
-			S.mode = 3;
-			if (e && e[0] >= '0' && e[0] <= '3') S.mode = e[0] - '0';
+			S.mode = 4;
+			if (e && e[0] >= '0' && e[0] <= '5') S.mode = e[0] - '0';
+			if (cudaFuncSetAttribute(k_solve_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+				cudaGetLastError();
+				if (S.mode == 5) S.mode = 3;
+			}
+			if (S.mode == 5 && occ < 1) S.mode = 3;
+			if (cudaFuncSetAttribute(k_solve_level_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
+				cudaGetLastError();
+				if (S.mode == 4) S.mode = 3;
+			}
 			if (S.mode == 1 && occ < 1) S.mode = 0;
 			const char *u = getenv("ADMMB_SOLVE_UNROLL");
 			if (u) { const int v = atoi(u); if (v == 8 || v == 16 || v == 32) S.unroll = v; }
@@ -709,6 +801,7 @@ int direct_setup(admmb_ctx *ctx) {
 			else if (S.unroll == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pf, k_solve_level_pf<16>, TILE_R, 0);
 			else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pf, k_solve_level_pf<8>, TILE_R, 0);
 			S.slots = sms * (occ_pf < 1 ? 1 : occ_pf);
+			if (const char *np = getenv("ADMMB_SOLVE_NO_PDL")) S.no_pdl = np[0] && np[0] != '0';
 			const char *sp = getenv("ADMMB_SOLVE_SPLIT");
 			if (sp) { const int v = atoi(sp); S.split = (v == 1) ? 1 : (v == 2) ? 2 : (v == 4) ? 3 : 0; }
 		}
@@ -729,13 +822,55 @@ int direct_solve(admmb_ctx *ctx) {
 	if (S.mode == 1 && !S.det) {
 		const int smem = PS_SMEM;
 		unsigned *gbar = reinterpret_cast<unsigned *>(S.d_y.p + 3 * (size_t)ctx->n);
-		k_solve_persistent<<<S.grid, PS_THREADS, smem, s>>>(S.d_tiles.p, S.d_data.p, S.d_pool.p, S.d_phase_first.p, S.d_phase_count.p,
+		k_solve_persistent<false><<<S.grid, PS_THREADS, smem, s>>>(S.d_tiles.p, S.d_data.p, S.d_pool.p, S.d_phase_first.p, S.d_phase_count.p,
 		                                                    S.n_phases, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, gbar, S.d_err.p);
 		ctx->launches++;
 		ADMMB_CUDA(ctx, cudaGetLastError());
 		return ADMMB_OK;
 	}
 	const int nl = S.F.nlevels;
+	if (S.mode == 4 && !S.det) {
+		// launch per level, tile by bulk copy; every launch after the first is programmatically dependent on the previous one
+		bool first = true;
+		for (int ph = 0; ph < 2 * nl; ++ph) {
+			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
+			const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
+			const int off = ph < nl ? S.fwd_first[lv] : S.bwd_first[lv];
+			if (cnt == 0) continue;
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(cnt); cfg.blockDim = dim3(LT_THREADS); cfg.dynamicSmemBytes = LT_SMEM; cfg.stream = s;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			attr[0].val.programmaticStreamSerializationAllowed = 1;
+			cfg.attrs = attr; cfg.numAttrs = (first || S.no_pdl) ? 0 : 1;
+			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_level_tma, (const SolveTile *)(S.d_tiles.p + off), (const double *)S.d_data.p,
+			                                   (const int *)S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p));
+			ctx->launches++;
+			first = false;
+		}
+		return ADMMB_OK;
+	}
+	if (S.mode == 5 && !S.det) {
+		// launch per level: resident CTAs stream the level's tiles through their bulk-copy ring; levels chained by PDL
+		bool first = true;
+		for (int ph = 0; ph < 2 * nl; ++ph) {
+			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
+			const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
+			if (cnt == 0) continue;
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(std::min(cnt, S.grid)); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = PS_SMEM; cfg.stream = s;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			attr[0].val.programmaticStreamSerializationAllowed = 1;
+			cfg.attrs = attr; cfg.numAttrs = (first || S.no_pdl) ? 0 : 1;
+			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_persistent<true>, (const SolveTile *)S.d_tiles.p, (const double *)S.d_data.p,
+			                                   (const int *)S.d_pool.p, (const int *)(S.d_phase_first.p + ph), (const int *)(S.d_phase_count.p + ph), 1,
+			                                   ctx->d_b.p, S.d_y.p, ctx->d_currx.p, (unsigned *)nullptr, S.d_err.p));
+			ctx->launches++;
+			first = false;
+		}
+		return ADMMB_OK;
+	}
 	if (S.mode == 2 && !S.det) {
 		// launch per level, each launch (after the first) programmatically dependent on the previous one
 		bool first = true;
