@@ -32,6 +32,8 @@ extern "C" int admmb_create(int device, admmb_ctx **out) {
 	ctx->device = device;
 	if (getenv("ADMMB_NO_GRAPH")) ctx->use_graph = false;
 	if (const char *e = getenv("ADMMB_DETERMINISTIC")) ctx->deterministic = e[0] && e[0] != '0';
+	if (const char *e = getenv("ADMMB_NO_FUSED_LOCAL")) ctx->fused_local = !(e[0] && e[0] != '0');
+	if (const char *e = getenv("ADMMB_NO_PDL")) ctx->use_pdl = !(e[0] && e[0] != '0');
 	e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return ADMMB_E_CUDA; }
 	*out = ctx;
@@ -356,7 +358,10 @@ extern "C" int admmb_finalize(admmb_ctx *ctx, double timestep_s) {
 		build_node_graph(ctx, gp, gi);
 		std::vector<int> blocks;
 		int leaf = 64; // dissection stops at sub-domains of this many nodes (= the leaf supernodes); ADMMB_ND_LEAF overrides (tuning knob)
-		if (const char *e = getenv("ADMMB_ND_LEAF")) { const int v = atoi(e); if (v >= 8 && v <= 1024) leaf = v; }
+		// small systems (the reference's shipped scenes: ~1 000 nodes): no dissection at all -- ONE dense supernode, so the
+		// solve is two launches (forward, backward) over a factor that lives in the L2 instead of 2 x 5 latency-bound levels
+		if (n <= 2048) leaf = n;
+		if (const char *e = getenv("ADMMB_ND_LEAF")) { const int v = atoi(e); if (v >= 8 && v <= 8192) leaf = v; }
 		compute_node_order(n, ctx->h_x0.data(), gp, gi, leaf, ctx->node_perm, blocks);
 		ctx->node_iperm.assign(n, -1);
 		for (int i = 0; i < n; ++i) ctx->node_iperm[ctx->node_perm[i]] = i;
@@ -505,12 +510,9 @@ static int solve_phase(admmb_ctx *ctx) {
 // One ADMM iteration (System.cpp:51-66): local step of every batch, right-hand side, solve.
 static int enqueue_iteration(admmb_ctx *ctx) {
 	const double dt2 = ctx->dt * ctx->dt;
-	for (Batch &b : ctx->batches) {
-		int rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
-		if (rc) return rc;
-	}
-	int rc = rhs_phase(ctx);
+	int rc = launch_local_all(ctx, ctx->d_currx.p);
 	if (rc) return rc;
+	if ((rc = rhs_phase(ctx))) return rc;
 	return solve_phase(ctx);
 }
 
@@ -561,7 +563,7 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 			size_t k = first;
 			for (int it = 0; it < admm_iters && !rc && e == cudaSuccess; ++it) {
 				e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
-				for (Batch &b : ctx->batches) if (!rc) rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
+				if (!rc) rc = launch_local_all(ctx, ctx->d_currx.p);
 				if (e == cudaSuccess) e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
 				if (!rc) rc = rhs_phase(ctx);
 				if (e == cudaSuccess) e = cudaEventRecordWithFlags(T.ev[k++], ctx->stream, cudaEventRecordExternal);
@@ -595,8 +597,8 @@ static int run_iterations(admmb_ctx *ctx, int admm_iters, const DumpTarget *dump
 			int rc = admmb_get_state(ctx, ADMMB_STATE_X, dump->x_it + (size_t)it * 3 * ctx->n);
 			if (rc) return rc;
 		}
-		for (Batch &b : ctx->batches) {
-			int rc = launch_local_step(ctx, b, ctx->d_currx.p, dt2);
+		{
+			int rc = launch_local_all(ctx, ctx->d_currx.p);
 			if (rc) return rc;
 		}
 		if (dump && dump->z_it) {
@@ -814,8 +816,7 @@ extern "C" int admmb_debug_local_step(admmb_ctx *ctx, const double *x3n) {
 	ADMMB_CUDA(ctx, cudaMemcpyAsync(ctx->d_io.p, ctx->h_pin, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	int rc = launch_permute_in(ctx, ctx->d_io.p, ctx->d_currx.p);
 	if (rc) return rc;
-	for (Batch &b : ctx->batches)
-		if ((rc = launch_local_step(ctx, b, ctx->d_currx.p, ctx->dt * ctx->dt))) return rc;
+	if ((rc = launch_local_all(ctx, ctx->d_currx.p))) return rc;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return ADMMB_OK;
 }

@@ -113,6 +113,9 @@ struct admmb_ctx {
 	cudaStream_t stream = nullptr;
 	std::string err;
 	bool finalized = false;
+	bool fused_local = true;    // small systems: all force batches in one launch (ADMMB_NO_FUSED_LOCAL=1 disables)
+	bool use_pdl = true;        // programmatic dependent launch between the kernels of an iteration (ADMMB_NO_PDL=1 disables)
+	bool solve_vectors_zeroed = false; // the right-hand-side kernel has just cleared y and curr_x for the direct solve
 	bool broken = false;        // a refactorisation failed after the new weights were uploaded: factor and weights disagree
 
 	int n = 0;
@@ -205,6 +208,8 @@ void assemble_system(admmb_ctx *ctx);
 void build_node_graph(const admmb_ctx *ctx, std::vector<int> &ptr, std::vector<int> &idx);
 // kernels_local.cu
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2);
+bool direct_vectors(admmb_ctx *ctx, double **y);           // direct_solve.cu
+int launch_local_all(admmb_ctx *ctx, const double *d_x);   // every batch: one fused launch for small systems
 int launch_explicit(admmb_ctx *ctx, ExplicitEntry &e); // subset ExplicitForce / WindForce on d_x, d_v
 int upload_explicit(admmb_ctx *ctx, ExplicitEntry &e); // after the node order is known
 // kernels_global.cu

@@ -570,6 +570,14 @@ void direct_set_blocks(admmb_ctx *ctx, const std::vector<int> &block_end) {
 	ctx->direct->block_end = block_end;
 }
 
+// y of the direct solve, for the right-hand-side kernel to clear (false: no direct solver set up, or the persistent
+// variant whose barrier counters sit behind y and need the memset)
+bool direct_vectors(admmb_ctx *ctx, double **y) {
+	if (!ctx->direct || !ctx->direct->d_y.p || ctx->direct->mode == 1) return false;
+	*y = ctx->direct->d_y.p;
+	return true;
+}
+
 void direct_fill_info(const admmb_ctx *ctx, admmb_info *out) {
 	if (!ctx->direct) return;
 	const DirectSolver &S = *ctx->direct;
@@ -817,8 +825,12 @@ int direct_solve(admmb_ctx *ctx) {
 	DirectSolver &S = *ctx->direct;
 	cudaStream_t s = ctx->stream;
 	const size_t bytes = 3 * (size_t)ctx->n * sizeof(double);
-	ADMMB_CUDA(ctx, cudaMemsetAsync(S.d_y.p, 0, S.d_y.bytes(), s)); // y and the phase barrier counters behind it
-	ADMMB_CUDA(ctx, cudaMemsetAsync(ctx->d_currx.p, 0, bytes, s));
+	const bool zeroed = ctx->solve_vectors_zeroed && S.mode != 1; // (mode 1 keeps its barrier counters behind y: always memset)
+	ctx->solve_vectors_zeroed = false;
+	if (!zeroed) {
+		ADMMB_CUDA(ctx, cudaMemsetAsync(S.d_y.p, 0, S.d_y.bytes(), s)); // y and the phase barrier counters behind it
+		ADMMB_CUDA(ctx, cudaMemsetAsync(ctx->d_currx.p, 0, bytes, s));
+	}
 	if (S.mode == 1 && !S.det) {
 		const int smem = PS_SMEM;
 		unsigned *gbar = reinterpret_cast<unsigned *>(S.d_y.p + 3 * (size_t)ctx->n);
@@ -842,7 +854,9 @@ int direct_solve(admmb_ctx *ctx) {
 			cudaLaunchAttribute attr[1];
 			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 			attr[0].val.programmaticStreamSerializationAllowed = 1;
-			cfg.attrs = attr; cfg.numAttrs = (first || S.no_pdl) ? 0 : 1;
+			// (the first level may follow the right-hand-side kernel programmatically too when that kernel has cleared the
+			// vectors itself: there is no memset node in between)
+			cfg.attrs = attr; cfg.numAttrs = ((first && !(zeroed && ctx->use_pdl)) || S.no_pdl) ? 0 : 1;
 			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_level_tma, (const SolveTile *)(S.d_tiles.p + off), (const double *)S.d_data.p,
 			                                   (const int *)S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p));
 			ctx->launches++;

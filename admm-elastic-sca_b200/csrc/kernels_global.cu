@@ -123,9 +123,13 @@ int launch_frame_end(admmb_ctx *ctx) {
 // b_v = M x_bar_v + sum over the (force, corner) slots incident to node v of P[slot]   -- gather, deterministic.
 __global__ void __launch_bounds__(VEC_THREADS) k_rhs_gather(int n, const int *__restrict__ vptr, const int *__restrict__ vslots,
                                                             const double *__restrict__ P, const double *__restrict__ Mxbar,
-                                                            double *__restrict__ b) {
+                                                            double *__restrict__ b, double *__restrict__ zero_y, double *__restrict__ zero_x) {
+	asm volatile("griddepcontrol.wait;" ::: "memory"); // every local kernel has completed (no-op without PDL)
 	const int v = blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= n) return;
+	// the direct solve accumulates into y and curr_x: cleared here instead of by two memset nodes per iteration
+	if (zero_y) { zero_y[3 * (size_t)v + 0] = 0.0; zero_y[3 * (size_t)v + 1] = 0.0; zero_y[3 * (size_t)v + 2] = 0.0; }
+	if (zero_x) { zero_x[3 * (size_t)v + 0] = 0.0; zero_x[3 * (size_t)v + 1] = 0.0; zero_x[3 * (size_t)v + 2] = 0.0; }
 	double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 	const int p1 = vptr[v + 1];
 	for (int p = vptr[v]; p < p1; ++p) {
@@ -139,10 +143,18 @@ __global__ void __launch_bounds__(VEC_THREADS) k_rhs_gather(int n, const int *__
 
 int launch_rhs(admmb_ctx *ctx) {
 	const int n = ctx->n;
-	k_rhs_gather<<<(n + VEC_THREADS - 1) / VEC_THREADS, VEC_THREADS, 0, ctx->stream>>>(n, ctx->d_vert_ptr.p, ctx->d_vert_slots.p, ctx->d_P.p,
-	                                                                               ctx->d_Mxbar.p, ctx->d_b.p);
+	double *zy = nullptr, *zx = nullptr;
+	if (ctx->solver == ADMMB_SOLVER_DIRECT && direct_vectors(ctx, &zy)) zx = ctx->d_currx.p;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((n + VEC_THREADS - 1) / VEC_THREADS); cfg.blockDim = dim3(VEC_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+	ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_rhs_gather, n, (const int *)ctx->d_vert_ptr.p, (const int *)ctx->d_vert_slots.p, (const double *)ctx->d_P.p,
+	                                   (const double *)ctx->d_Mxbar.p, ctx->d_b.p, zy, zx));
+	ctx->solve_vectors_zeroed = (zx != nullptr);
 	ctx->launches++;
-	ADMMB_CUDA(ctx, cudaGetLastError());
 	return ADMMB_OK;
 }
 

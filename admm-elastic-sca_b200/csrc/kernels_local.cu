@@ -66,6 +66,53 @@ __global__ void __launch_bounds__(LOCAL_THREADS) k_local_collision(const LocalAr
 	if (e < a.count) local_collision(a, e);
 }
 
+// ---- small scenes: every force batch of the ADMM iteration in ONE launch ---------------------------------------------
+// The reference's shipped scenes have 2.5-6 k elements in 1-3 force classes: each per-class kernel is a handful of CTAs
+// and an iteration is bound by launch latency, not by work.  One kernel walks all batches (block range -> batch -> the
+// same per-force body as the per-class kernels), launched with programmatic dependent launch so that its CTAs are already
+// resident when the previous iteration's solve drains.  Used when the system has at most FUSED_MAX_FORCES forces.
+#define FUSED_MAX 8
+#define FUSED_MAX_FORCES 32768
+struct FusedArgs {
+	int nb;
+	int block_first[FUSED_MAX + 1];
+	int type[FUSED_MAX], kind[FUSED_MAX];
+	LocalArgs a[FUSED_MAX];
+};
+__global__ void __launch_bounds__(LOCAL_THREADS) k_local_fused(const __grid_constant__ FusedArgs F) {
+	asm volatile("griddepcontrol.wait;" ::: "memory"); // curr_x of the previous solve is complete (no-op without PDL)
+	__shared__ double park[PARK_SLOTS * LOCAL_THREADS];
+	int b = 0;
+	while (b + 1 < F.nb && (int)blockIdx.x >= F.block_first[b + 1]) ++b;
+	const LocalArgs &a = F.a[b];
+	const int e = ((int)blockIdx.x - F.block_first[b]) * LOCAL_THREADS + threadIdx.x;
+	if (e >= a.count) return;
+	const int kind = F.kind[b];
+	switch (F.type[b]) {
+	case BT_TETS:
+		if (kind == ADMMB_TET_LINEAR_STRAIN) local_tet<ADMMB_TET_LINEAR_STRAIN, 1>(a, e);
+		else if (kind == ADMMB_TET_VOLUME) local_tet<ADMMB_TET_VOLUME, 1>(a, e);
+		else if (kind == ADMMB_TET_NEOHOOKEAN) {
+			if (a.max_iterations <= 5) local_tet_hyper<NHModel, 5>(a, e, park + threadIdx.x, LOCAL_THREADS);
+			else local_tet_hyper<NHModel, 10>(a, e, park + threadIdx.x, LOCAL_THREADS);
+		} else {
+			if (a.max_iterations <= 5) local_tet_hyper<StVKModel, 5>(a, e, park + threadIdx.x, LOCAL_THREADS);
+			else local_tet_hyper<StVKModel, 10>(a, e, park + threadIdx.x, LOCAL_THREADS);
+		}
+		break;
+	case BT_TRIS:
+		if (kind == ADMMB_TRI_LIMITED_STRAIN) local_tri<ADMMB_TRI_LIMITED_STRAIN>(a, e);
+		else if (kind == ADMMB_TRI_AREA) local_tri<ADMMB_TRI_AREA>(a, e);
+		else local_tri<ADMMB_TRI_FUNG>(a, e);
+		break;
+	case BT_SPRINGS: local_spring(a, e); break;
+	case BT_BENDS: local_bend(a, e); break;
+	case BT_STATIC_ANCHORS:
+	case BT_MOVING_ANCHORS: local_anchor(a, e); break;
+	case BT_COLLISION: local_collision(a, e); break;
+	}
+}
+
 #define HYPER_SMEM (PARK_SLOTS * HYPER_THREADS * sizeof(double))
 // the hyperelastic kernels park more than the default 48 KB of dynamic shared memory per block: opt in, once per device
 static int hyper_smem_opt_in(admmb_ctx *ctx) {
@@ -79,14 +126,7 @@ static int hyper_smem_opt_in(admmb_ctx *ctx) {
 	return ADMMB_OK;
 }
 
-int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
-	(void)dt2;
-	if (b.nlocal == 0) return ADMMB_OK;
-	if (b.type == BT_TETS && (b.kind == ADMMB_TET_NEOHOOKEAN || b.kind == ADMMB_TET_STVK)) {
-		int rc = hyper_smem_opt_in(ctx);
-		if (rc) return rc;
-	}
-	LocalArgs a;
+static void fill_local_args(admmb_ctx *ctx, Batch &b, const double *d_x, LocalArgs &a) {
 	memset(&a, 0, sizeof(a));
 	a.count = b.nlocal;
 	a.idx = b.d_idx.p; a.S = b.d_S.p; a.w = b.d_w.p; a.wdt2 = b.d_wdt2.p; a.kk = b.d_kk.p; a.aux = b.d_aux.p;
@@ -96,6 +136,53 @@ int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
 	a.p0 = b.p0; a.p1 = b.p1; a.p2 = b.p2; a.max_iterations = b.max_iterations; a.flag = b.flag;
 	a.kprox = std::min(b.p0, b.p1);
 	a.shape_kind = b.d_shape_kind.p; a.shape_params = b.d_shape_params.p; a.nshapes = (int)b.shape_kind.size();
+}
+
+// The local step of every batch (System.cpp:57-58).  Small systems: one fused launch; otherwise one launch per batch.
+int launch_local_all(admmb_ctx *ctx, const double *d_x) {
+	long total = 0;
+	int nb = 0;
+	for (Batch &b : ctx->batches) { total += b.nlocal; nb += b.nlocal > 0; }
+	if (nb == 0) return ADMMB_OK;
+	if (ctx->fused_local && nb <= FUSED_MAX && total <= FUSED_MAX_FORCES) {
+		FusedArgs F;
+		memset(&F, 0, sizeof(F));
+		int blocks = 0;
+		for (Batch &b : ctx->batches) {
+			if (b.nlocal == 0) continue;
+			F.block_first[F.nb] = blocks;
+			F.type[F.nb] = b.type; F.kind[F.nb] = b.kind;
+			fill_local_args(ctx, b, d_x, F.a[F.nb]);
+			blocks += (b.nlocal + LOCAL_THREADS - 1) / LOCAL_THREADS;
+			F.nb++;
+		}
+		F.block_first[F.nb] = blocks;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(LOCAL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+		ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_local_fused, F));
+		ctx->launches++;
+		return ADMMB_OK;
+	}
+	for (Batch &b : ctx->batches) {
+		int rc = launch_local_step(ctx, b, d_x, 0.0);
+		if (rc) return rc;
+	}
+	return ADMMB_OK;
+}
+
+int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2) {
+	(void)dt2;
+	if (b.nlocal == 0) return ADMMB_OK;
+	if (b.type == BT_TETS && (b.kind == ADMMB_TET_NEOHOOKEAN || b.kind == ADMMB_TET_STVK)) {
+		int rc = hyper_smem_opt_in(ctx);
+		if (rc) return rc;
+	}
+	LocalArgs a;
+	fill_local_args(ctx, b, d_x, a);
 	const int grid = (b.nlocal + LOCAL_THREADS - 1) / LOCAL_THREADS;
 	cudaStream_t s = ctx->stream;
 	switch (b.type) {
