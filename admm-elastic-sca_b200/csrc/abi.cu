@@ -495,15 +495,17 @@ static int rhs_phase(admmb_ctx *ctx) {
 	if (ctx->dist_world > 1 && ctx->solver == ADMMB_SOLVER_DIRECT) rc = dist_allgather_nodes(ctx, ctx->d_b.p);
 	return rc;
 }
-// Solve (System.cpp:62).  The replicated direct solve accumulates with floating-point atomics by default, so the ranks'
-// solutions agree only to rounding; every rank therefore keeps ITS chunk and the chunks are all-gathered: all ranks hold
-// the same curr_x bit for bit (a boundary force evaluated on two ranks sees identical inputs), for 20 us per iteration.
-// With the deterministic solve the ranks' solutions are already identical and the exchange is skipped.
+// Solve (System.cpp:62).  Partitioned mesh, direct solver: by default the solve is sharded by subtrees of the elimination
+// tree (direct_solve.cu: every rank streams only its subtrees' tiles and the replicated top of the tree, one small
+// all-reduce of the top rows in between, one all-reduce of x at the end -- all ranks hold the same curr_x bit for bit).
+// With ADMMB_DIST_SOLVE=replicated every rank solves the whole system; the default (atomic) solve then agrees between ranks
+// only to rounding, so every rank keeps ITS chunk and the chunks are all-gathered.  With the deterministic solve (always
+// replicated) the ranks' solutions are already identical and the exchange is skipped.
 static int solve_phase(admmb_ctx *ctx) {
 	if (ctx->solver == ADMMB_SOLVER_PCG) return pcg_solve(ctx);
 	int rc = direct_solve(ctx);
 	if (rc) return rc;
-	if (ctx->dist_world > 1 && !ctx->deterministic) rc = dist_allgather_nodes(ctx, ctx->d_currx.p);
+	if (ctx->dist_world > 1 && !ctx->deterministic && !direct_is_sharded(ctx)) rc = dist_allgather_nodes(ctx, ctx->d_currx.p);
 	return rc;
 }
 

@@ -209,6 +209,7 @@ void build_node_graph(const admmb_ctx *ctx, std::vector<int> &ptr, std::vector<i
 // kernels_local.cu
 int launch_local_step(admmb_ctx *ctx, Batch &b, const double *d_x, double dt2);
 bool direct_vectors(admmb_ctx *ctx, double **y);           // direct_solve.cu
+bool direct_is_sharded(const admmb_ctx *ctx);              // partitioned mesh: the solve itself is sharded (it ends with its own all-reduce of x)
 int launch_local_all(admmb_ctx *ctx, const double *d_x);   // every batch: one fused launch for small systems
 int launch_explicit(admmb_ctx *ctx, ExplicitEntry &e); // subset ExplicitForce / WindForce on d_x, d_v
 int upload_explicit(admmb_ctx *ctx, ExplicitEntry &e); // after the node order is known

@@ -56,6 +56,17 @@ struct DirectSolver {
 	int slots = 0;   // resident CTAs of the per-level kernel on the whole device
 	int split = 0;   // ADMMB_SOLVE_SPLIT: 0 = choose per level, else log2 of the forced column split + 1
 	bool no_pdl = false; // ADMMB_SOLVE_NO_PDL=1: mode 4 without programmatic dependent launch (A/B)
+	// One mesh over several ranks, solve sharded by subtrees of the elimination tree (see shard_owners): this rank holds
+	// the tiles of ITS subtrees and of the replicated top of the tree only.  Phases, each a list of per-level tile ranges:
+	// own subtrees forward -> all-reduce of the top rows of b -> top forward -> top backward -> own subtrees backward ->
+	// all-reduce of x.
+	bool sharded = false;
+	struct Range { int first, count; };
+	std::vector<Range> sh_sub_fwd, sh_top_fwd, sh_top_bwd, sh_sub_bwd;
+	DevBuf<int> d_top_rows;    // nodes (columns) of the replicated top supernodes
+	DevBuf<double> d_top_buf;  // their 3 coordinates, packed for the all-reduce
+	int n_top_rows = 0;
+	double top_fraction = 0.0; // share of the factor that is replicated
 	// bit-reproducible variant (ctx->deterministic): tiles store their partial sums, a second kernel per level adds them
 	// to the vectors in a fixed order (no floating-point atomics)
 	bool det = false;
@@ -661,6 +672,90 @@ static void fill_backward(const TilePlan &p, double *dst) {
 	for (size_t i = (size_t)t.nrows * t.ncols; i < align16((size_t)t.nrows * t.ncols); ++i) dst[i] = 0.0;
 }
 
+// Subtree-to-rank mapping of the supernodal elimination tree (the classic way to parallelise a sparse triangular solve):
+// the tree is cut near its root; everything above the cut (the largest separators) is processed by EVERY rank, each
+// subtree below it by ONE rank.  Subtrees only couple through the rows of their common ancestors, so the forward pass
+// needs one all-reduce of those (few) rows and the backward pass none.  The cut is chosen by repeatedly opening the
+// heaviest subtree and keeping the configuration that minimises (replicated bytes + heaviest rank's bytes), the
+// bandwidth cost of the slowest rank.  owner[J] = rank, or -1 for the replicated top.
+static std::vector<int> shard_owners(const SupernodalFactor &F, int world, double *top_fraction) {
+	const int nb = F.nb;
+	std::vector<double> wgt(nb), sub(nb, 0.0);
+	std::vector<std::vector<int> > kids(nb);
+	double total = 0.0;
+	for (int J = 0; J < nb; ++J) {
+		const double w = F.start[J + 1] - F.start[J], r = F.rptr[J + 1] - F.rptr[J];
+		wgt[J] = (w + r) * w;
+		total += wgt[J];
+	}
+	for (int J = 0; J < nb; ++J) { // children precede their parents in elimination order
+		sub[J] += wgt[J];
+		if (F.parent[J] >= 0) { sub[F.parent[J]] += sub[J]; kids[F.parent[J]].push_back(J); }
+	}
+	std::vector<char> is_top(nb, 0);
+	std::vector<int> cand;
+	for (int J = 0; J < nb; ++J) if (F.parent[J] < 0) cand.push_back(J);
+	auto lpt = [&](const std::vector<int> &c, std::vector<int> *assign) {
+		std::vector<int> order(c);
+		std::sort(order.begin(), order.end(), [&](int a, int b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
+		std::vector<double> load(world, 0.0);
+		if (assign) assign->assign(nb, -2);
+		for (int J : order) {
+			int r = 0;
+			for (int q = 1; q < world; ++q) if (load[q] < load[r]) r = q;
+			load[r] += sub[J];
+			if (assign) (*assign)[J] = r;
+		}
+		return *std::max_element(load.begin(), load.end());
+	};
+	double top_w = 0.0, best = 1e300;
+	std::vector<char> best_top;
+	std::vector<int> best_cand;
+	for (int it = 0; it < 64 * world; ++it) {
+		const double cost = top_w + lpt(cand, nullptr);
+		if ((int)cand.size() >= world && cost < best) { best = cost; best_top = is_top; best_cand = cand; }
+		int h = -1;
+		for (size_t i = 0; i < cand.size(); ++i) if (!kids[cand[i]].empty() && (h < 0 || sub[cand[i]] > sub[cand[h]])) h = (int)i;
+		if (h < 0) break;
+		const int J = cand[h];
+		is_top[J] = 1;
+		top_w += wgt[J];
+		cand.erase(cand.begin() + h);
+		cand.insert(cand.end(), kids[J].begin(), kids[J].end());
+	}
+	std::vector<int> owner(nb, -1);
+	if (best_cand.empty()) { if (top_fraction) *top_fraction = 1.0; return owner; } // cannot be cut: everything replicated
+	std::vector<int> assign;
+	lpt(best_cand, &assign);
+	for (int J = nb - 1; J >= 0; --J) { // parents before children
+		if (best_top[J]) owner[J] = -1;
+		else if (assign[J] >= 0) owner[J] = assign[J];
+		else owner[J] = (F.parent[J] >= 0) ? owner[F.parent[J]] : 0;
+	}
+	double tw = 0.0;
+	for (int J = 0; J < nb; ++J) if (owner[J] < 0) tw += wgt[J];
+	if (top_fraction) *top_fraction = total > 0.0 ? tw / total : 1.0;
+	return owner;
+}
+
+__global__ void k_rows_zero(int cnt, const int *__restrict__ rows, double *v) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 3 * cnt) return;
+	v[3 * (size_t)rows[i / 3] + i % 3] = 0.0;
+}
+__global__ void k_rows_pack(int cnt, const int *__restrict__ rows, const double *__restrict__ v, double *__restrict__ buf) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 3 * cnt) return;
+	buf[i] = v[3 * (size_t)rows[i / 3] + i % 3];
+}
+__global__ void k_rows_unpack(int cnt, const int *__restrict__ rows, const double *__restrict__ buf, double *__restrict__ v) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 3 * cnt) return;
+	v[3 * (size_t)rows[i / 3] + i % 3] = buf[i];
+}
+
+bool direct_is_sharded(const admmb_ctx *ctx) { return ctx->direct && ctx->direct->sharded; }
+
 int direct_setup(admmb_ctx *ctx) {
 	if (!ctx->direct) ADMMB_FAIL(ctx, ADMMB_E_STATE, "no dissection blocks (finalize order)");
 	DirectSolver &S = *ctx->direct;
@@ -685,6 +780,35 @@ int direct_setup(admmb_ctx *ctx) {
 	std::vector<TilePlan> fplan, bplan;
 	size_t fsz = 0, bsz = 0;
 	std::vector<int> f_first(F.nlevels), f_count(F.nlevels), b_first(F.nlevels), b_count(F.nlevels);
+	// a mesh partitioned over ranks: shard the solve by subtrees unless the bit-reproducible solve was asked for (its
+	// reduction tables assume the whole tree) or ADMMB_DIST_SOLVE=replicated
+	S.sharded = ctx->dist_world > 1 && !ctx->deterministic;
+	if (const char *e = getenv("ADMMB_DIST_SOLVE")) if (e[0] == 'r') S.sharded = false;
+	std::vector<int> owner;
+	std::vector<DirectSolver::Range> shf_sub, shf_top, shb_sub, shb_top; // per level, tile indices within fplan / bplan
+	if (S.sharded) {
+		owner = shard_owners(F, ctx->dist_world, &S.top_fraction);
+		for (int pass = 0; pass < 2; ++pass) // own subtrees first, then the replicated top: two contiguous tile ranges per level
+			for (int lv = 0; lv < F.nlevels; ++lv) {
+				const int f0 = (int)fplan.size(), b0 = (int)bplan.size();
+				for (int J : by_level[lv])
+					if (pass == 0 ? owner[J] == ctx->dist_rank : owner[J] < 0) plan_supernode(F, J, fsz, fplan, bsz, bplan);
+				const int fc = (int)fplan.size() - f0, bc = (int)bplan.size() - b0;
+				if (fc) (pass == 0 ? shf_sub : shf_top).push_back(DirectSolver::Range{ f0, fc });
+				if (bc) (pass == 0 ? shb_sub : shb_top).push_back(DirectSolver::Range{ b0, bc });
+			}
+		std::vector<int> top_rows;
+		for (int J = 0; J < F.nb; ++J)
+			if (owner[J] < 0) for (int c = F.start[J]; c < F.start[J + 1]; ++c) top_rows.push_back(c);
+		S.n_top_rows = (int)top_rows.size();
+		ADMMB_CUDA(ctx, S.d_top_rows.alloc(std::max<size_t>(top_rows.size(), 1)));
+		ADMMB_CUDA(ctx, S.d_top_rows.upload(top_rows.data(), top_rows.size(), ctx->stream));
+		ADMMB_CUDA(ctx, S.d_top_buf.alloc(3 * std::max<size_t>(top_rows.size(), 1)));
+		ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		// (the per-level arrays of the unsharded paths stay empty: those paths are not taken)
+		std::fill(f_count.begin(), f_count.end(), 0);
+		std::fill(b_count.begin(), b_count.end(), 0);
+	} else
 	for (int lv = 0; lv < F.nlevels; ++lv) {
 		f_first[lv] = (int)fplan.size();
 		b_first[lv] = (int)bplan.size();
@@ -770,6 +894,17 @@ int direct_setup(admmb_ctx *ctx) {
 	S.fwd_first = f_first; S.fwd_count = f_count;
 	S.bwd_first.resize(F.nlevels); S.bwd_count = b_count;
 	for (int lv = 0; lv < F.nlevels; ++lv) S.bwd_first[lv] = (int)ftiles.size() + b_first[lv];
+	if (S.sharded) {
+		// forward: levels ascending; backward: levels descending, and its tiles sit behind the forward tiles in d_tiles
+		S.sh_sub_fwd = shf_sub;
+		S.sh_top_fwd = shf_top;
+		S.sh_top_bwd.assign(shb_top.rbegin(), shb_top.rend());
+		S.sh_sub_bwd.assign(shb_sub.rbegin(), shb_sub.rend());
+		for (auto &r : S.sh_top_bwd) r.first += (int)ftiles.size();
+		for (auto &r : S.sh_sub_bwd) r.first += (int)ftiles.size();
+		if (verbose) fprintf(stderr, "[setup] rank %d: sharded solve, %.1f %% of the factor replicated, %zu + %zu own / top forward levels, %d top rows\n",
+		                     ctx->dist_rank, 100.0 * S.top_fraction, S.sh_sub_fwd.size(), S.sh_top_fwd.size(), S.n_top_rows);
+	}
 	// persistent kernel schedule: forward levels ascending, then backward levels descending
 	{
 		std::vector<int> pf, pc;
@@ -802,6 +937,7 @@ int direct_setup(admmb_ctx *ctx) {
 				if (S.mode == 4) S.mode = 3;
 			}
 			if (S.mode == 1 && occ < 1) S.mode = 0;
+			if (S.sharded && S.mode != 4) ADMMB_FAIL(ctx, ADMMB_E_STATE, "the sharded solve of a partitioned mesh needs solve mode 4 (ADMMB_DIST_SOLVE=replicated selects the replicated solve)");
 			const char *u = getenv("ADMMB_SOLVE_UNROLL");
 			if (u) { const int v = atoi(u); if (v == 8 || v == 16 || v == 32) S.unroll = v; }
 			int occ_pf = 0;
@@ -841,6 +977,41 @@ int direct_solve(admmb_ctx *ctx) {
 		return ADMMB_OK;
 	}
 	const int nl = S.F.nlevels;
+	if (S.sharded) {
+		// own subtrees forward -> all-reduce of the top rows of b -> top forward / backward (every rank) -> own subtrees
+		// backward -> all-reduce of x (every row has exactly one non-zero contribution: the sum is exact and identical on all ranks)
+		bool chain = zeroed && ctx->use_pdl && !S.no_pdl; // may the next level launch follow its predecessor programmatically?
+		auto level = [&](const DirectSolver::Range &r) -> int {
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(r.count); cfg.blockDim = dim3(LT_THREADS); cfg.dynamicSmemBytes = LT_SMEM; cfg.stream = s;
+			cudaLaunchAttribute attr[1];
+			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			attr[0].val.programmaticStreamSerializationAllowed = 1;
+			cfg.attrs = attr; cfg.numAttrs = chain ? 1 : 0;
+			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_level_tma, (const SolveTile *)(S.d_tiles.p + r.first), (const double *)S.d_data.p,
+			                                   (const int *)S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p));
+			ctx->launches++;
+			chain = ctx->use_pdl && !S.no_pdl;
+			return ADMMB_OK;
+		};
+		const int nt = S.n_top_rows, g = (3 * nt + 255) / 256;
+		int rc;
+		if (ctx->dist_rank > 0 && nt > 0) { k_rows_zero<<<g, 256, 0, s>>>(nt, S.d_top_rows.p, ctx->d_b.p); ctx->launches++; chain = false; }
+		for (const auto &r : S.sh_sub_fwd) if ((rc = level(r))) return rc;
+		if (nt > 0) {
+			k_rows_pack<<<g, 256, 0, s>>>(nt, S.d_top_rows.p, ctx->d_b.p, S.d_top_buf.p);
+			if ((rc = dist_allreduce_sum(ctx, S.d_top_buf.p, 3 * nt))) return rc;
+			k_rows_unpack<<<g, 256, 0, s>>>(nt, S.d_top_rows.p, S.d_top_buf.p, ctx->d_b.p);
+			ctx->launches += 2;
+			chain = false;
+		}
+		for (const auto &r : S.sh_top_fwd) if ((rc = level(r))) return rc;
+		for (const auto &r : S.sh_top_bwd) if ((rc = level(r))) return rc;
+		for (const auto &r : S.sh_sub_bwd) if ((rc = level(r))) return rc;
+		if (ctx->dist_rank > 0 && nt > 0) { k_rows_zero<<<g, 256, 0, s>>>(nt, S.d_top_rows.p, ctx->d_currx.p); ctx->launches++; }
+		ADMMB_CUDA(ctx, cudaGetLastError());
+		return dist_allreduce_sum(ctx, ctx->d_currx.p, 3 * ctx->n);
+	}
 	if (S.mode == 4 && !S.det) {
 		// launch per level, tile by bulk copy; every launch after the first is programmatically dependent on the previous one
 		bool first = true;
@@ -942,6 +1113,7 @@ void direct_destroy(admmb_ctx *ctx) {
 	if (!ctx->direct) return;
 	DirectSolver &S = *ctx->direct;
 	S.d_data.free(); S.d_tiles.free(); S.d_pool.free(); S.d_y.free(); S.d_phase_first.free(); S.d_phase_count.free(); S.d_err.free();
+	S.d_top_rows.free(); S.d_top_buf.free();
 	S.d_part.free(); S.d_red_key.free(); S.d_red_ptr.free(); S.d_red_slot.free(); S.d_red_tgt.free(); S.d_red_counter.free();
 	delete ctx->direct;
 	ctx->direct = nullptr;

@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--solver", default="direct", choices=["direct", "pcg"])
     ap.add_argument("--partition", default="auto", choices=["auto", "off", "only", "pcg"],
                     help="N > 1: besides the scene ensemble (`value`), time ONE mesh partitioned over the ranks (local step partitioned, right-hand "
-                         "side all-gathered, direct solve replicated) and report it as `partition` (strong scaling); 'only' makes it the headline; "
+                         "side all-gathered, direct solve sharded by elimination subtrees) and report it as `partition` (strong scaling); "
                          "'pcg' = partitioned Jacobi-PCG rows instead of the replicated direct solve")
     args = ap.parse_args()
 
@@ -523,8 +523,10 @@ def main():
         pit = max(pph["iters"], 1)
         partition = {"value": args.steps * iters_per_frame / (pms_max * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_step": pms_max / args.steps,
                      "mode": "local step partitioned by elements; " + ("Jacobi-PCG rows partitioned, NCCL all-gather + all-reduce per CG iteration" if args.partition == "pcg"
-                                                                      else "right-hand side all-gathered (ncclAllGather of 3n doubles per ADMM iteration), direct solve replicated on every rank"),
-                     "phases_ms_per_iteration_rank0": {"local": pph["local_ms"] / pit, "rhs_and_allgather": pph["rhs_ms"] / pit, "solve": pph["solve_ms"] / pit},
+                                                                      else "right-hand side all-gathered (ncclAllGather of 3n doubles per ADMM iteration); direct solve sharded by subtrees of the elimination tree "
+                                                                           "(each rank streams its subtrees' factor tiles + the replicated top separators; one small all-reduce of the top rows, one all-reduce of x)"),
+                     "phases_ms_per_iteration_rank0": {"local": pph["local_ms"] / pit, "rhs_and_allgather": pph["rhs_ms"] / pit, "solve_and_allreduce": pph["solve_ms"] / pit},
+                     "factor_bytes_rank0": psim.info()["factor_bytes"], "factor_bytes_single_gpu": info0["factor_bytes"],
                      "gpu_launches_rank0": int(planches), "replica_it_s_per_gpu": value / world}
         psim.close()
 

@@ -1,7 +1,8 @@
 """One mesh partitioned over two GPUs.  Needs two CUDA devices (gpurun --gpus 2); skipped otherwise.
 
 * direct solver: the local step is partitioned (every rank evaluates the forces that touch its chunk of the nodes), the owned
-  rows of the right-hand side are all-gathered and every rank solves redundantly.  The owned rows are summed from the same
+  rows of the right-hand side are all-gathered; the solve is sharded by subtrees of the elimination tree (default) or, with
+  the deterministic solve, run redundantly by every rank.  The owned rows are summed from the same
   slots in the same order as on one GPU, so with the deterministic solve the partitioned run must reproduce the single-GPU run
   BIT FOR BIT (positions, and z / u / optimiser state merged from the ranks' exports); with the default (atomic) solve the ranks
   must still agree with each other bit for bit (their solution chunks are exchanged) and with one GPU to rounding.
@@ -100,10 +101,14 @@ def test_two_rank_direct_deterministic_is_bit_identical_to_one_gpu(kind, label):
         assert np.array_equal(_merge(res[0][5], res[1][5]), sr)
 
 
-def test_two_rank_direct_default_solve_ranks_identical():
+@pytest.mark.parametrize("N", [10, 16])
+def test_two_rank_direct_default_solve_ranks_identical(N):
+    """Default solve of a partitioned mesh: sharded by subtrees of the elimination tree (N=16: 4 913 nodes, a real nested
+    dissection tree cut below its root separator; N=10: 1 331 nodes form ONE dense supernode, nothing to cut -- the
+    degenerate case where everything is the replicated top)."""
     _need_two()
     import admm_b200
-    kw = dict(N=10, kind=scenes.TET_ARAP, seed=31)
+    kw = dict(N=N, kind=scenes.TET_ARAP, seed=31)
     frames = 3
     xr = _single(kw, frames, admm_b200.SOLVER_DIRECT, False)[0]
     res = _two_ranks(kw, frames, admm_b200.SOLVER_DIRECT, False)
