@@ -394,17 +394,19 @@ __device__ __forceinline__ double load_rhs_elem(const SolveTile &t, const int *_
 // of level p + 1 start as soon as every CTA of level p is resident, so their tiles stream in during the tail of level p
 // instead of after it.  256 threads multiply the tile from shared memory (4 column groups x 64 rows).
 // ---------------------------------------------------------------------------------------------------------
+#ifndef LT_THREADS
 #define LT_THREADS 256
+#endif
 #define LT_GROUPS (LT_THREADS / TILE_R)
-#define LT_SMEM (PS_TILE_BYTES + TILE_C * 3 * 8 + LT_GROUPS * TILE_R * 3 * 8 + 16)
+#define LT_SMEM (PS_TILE_BYTES + TILE_C * 3 * 8 + 16) // 34 320 B: six CTAs per SM (the partial sums reuse the tile's storage)
 
 __global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
                                                                 const int *__restrict__ pool, double *vb, double *vy, double *vx) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	double *tile = reinterpret_cast<double *>(smem_raw);                   // 64 x 64, column-major, ld = nrows
 	double *sv = tile + TILE_R * TILE_C;                                    // TILE_C x 3
-	double *part = sv + TILE_C * 3;                                         // LT_GROUPS x 64 x 3 partial sums
-	unsigned long long *full = reinterpret_cast<unsigned long long *>(part + LT_GROUPS * TILE_R * 3);
+	double *part = tile;                                                    // LT_GROUPS x 64 x 3 partial sums, once the tile has been consumed
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(sv + TILE_C * 3);
 	const int tid = threadIdx.x;
 	const SolveTile t = tiles[blockIdx.x];
 	if (tid == 0) {
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile 
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	double *vecs[3] = { vb, vy, vx };
 	// index lists do not depend on the previous level
+	static_assert(LT_THREADS >= 3 * TILE_C, "one thread per right-hand-side element of the tile");
 	int gi = 0;
 	const int c_in = tid / 3, k_in = tid - 3 * c_in;
 	if (tid < 3 * t.ncols) gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c_in] : t.in_idx + c_in;
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile 
 				a2 += m * sv[3 * c + 2];
 			}
 		}
+		__syncthreads(); // every thread has read its part of the tile: its storage now takes the partial sums
 		part[(grp * TILE_R + row) * 3 + 0] = a0;
 		part[(grp * TILE_R + row) * 3 + 1] = a1;
 		part[(grp * TILE_R + row) * 3 + 2] = a2;
@@ -449,7 +453,9 @@ __global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile 
 	__syncthreads();
 	if (tid < 3 * t.nrows) {
 		const int r = tid / 3, k = tid - 3 * r;
-		double a = (part[(0 * TILE_R + r) * 3 + k] + part[(1 * TILE_R + r) * 3 + k]) + (part[(2 * TILE_R + r) * 3 + k] + part[(3 * TILE_R + r) * 3 + k]);
+		double a = part[(0 * TILE_R + r) * 3 + k];
+#pragma unroll
+		for (int gq = 1; gq < LT_GROUPS; ++gq) a += part[(gq * TILE_R + r) * 3 + k];
 		if (t.flags & TF_NEG) a = -a;
 		red_add(vecs[(t.flags >> TF_OUT_SHIFT) & 3] + 3 * (size_t)go + k, a);
 	}

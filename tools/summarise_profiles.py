@@ -24,9 +24,9 @@ def launches():
         a["us"] += k["gpu__time_duration.sum"] / 1e3
         a["mb"] += (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) / 1e6
     tot = sum(a["us"] for a in agg.values())
-    out = [f"profiles/{tag}_launches.txt -- ncu launch list, steady state (20 warm-up frames), 3 consecutive ADMM iterations of the 998,250-tet cube",
-           "command: tools/profile_round.sh (ADMMB_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__grid_size "
-           "--clock-control none -s <warm-up launches> -c <3 iterations> --csv python bench.py --cube 55 --steps 2 --warmup 20)",
+    out = [f"profiles/{tag}_launches.txt -- ncu launch list of ONE steady-state frame (10 ADMM iterations) of the 998,250-tet cube, after 20 conditioning + 5 warm-up frames",
+           "command: tools/profile_round.sh (ADMMB_NO_GRAPH=1 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__grid_size "
+           "--clock-control none --csv python bench.py --cube 55 --steps 1 --warmup 5 --no-cpu-baseline --no-pairs --profile-region)",
            f"(cold-cache, serialised per-launch times: compare SHARES with bench.py's phases_ms_per_iteration, not absolutes; raw CSV: {tag}_launches_ncu.csv)",
            "%-48s %8s %10s %7s %10s %8s" % ("kernel", "launches", "time us", "share", "DRAM MB", "GB/s")]
     for nm, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
@@ -59,7 +59,7 @@ def local():
     r = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
     out = [f"profiles/{tag}_local.txt -- ncu --set full --clock-control none --import-source on, one launch of the hyperelastic local-step kernel, 998,250-tet cube,",
-           "steady state after 20 warm-up frames (22 objective evaluations / tet); tools/profile_round.sh + tools/summarise_profiles.py", ""]
+           "frame 26 (20 conditioning + 5 warm-up frames: the regime bench.py times), 5th ADMM iteration of the frame; tools/profile_round.sh + tools/summarise_profiles.py", ""]
     for m in LOCAL_METRICS + [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]:
         if m in ix:
             out.append("%-95s %s" % (m, r[ix[m]]))
@@ -92,6 +92,8 @@ def solve():
 
 
 if __name__ == "__main__":
+    import os
     launches()
     local()
-    solve()
+    if os.path.exists(f"{G}/prof_solve_{tag}.ncu-rep"):
+        solve()
