@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of the dissection leaf size (levels vs factor bytes) with the prefetching solve kernel
-for leaf in ${LEAVES:-32 48 64 96 128 256}; do
-  ADMMB_ND_LEAF=$leaf ADMMB_SOLVE_MODE=${MODE:-3} python bench.py --cube ${CUBE:-55} --steps 10 --warmup 20 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); p=d['phases_ms_per_iteration']; s=d['setup']; print('leaf=$leaf value %7.1f local %.3f rhs %.3f solve %.3f  nnzL %.1fM factor %.2fs frac %.2f' % (d['value'], p['local'], p['rhs'], p['solve'], s['nnz_L']/1e6, s['factor_seconds'], d['roofline']['frac']))"
-done
+# nested-dissection leaf size (levels vs fill) with the bulk-copy solve kernel
+cd $GRAFT_REPO_ROOT
+for N in 30 55; do
+for leaf in 64 128 256; do
+  ADMMB_ND_LEAF=$leaf python bench.py --cube $N --steps 20 --warmup 5 --no-cpu-baseline --no-pairs 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); p=d['phases_ms_per_iteration']; print('N=$N leaf %4d value %7.1f  local %.3f rhs %.3f solve %.3f  step %.4f  levels %d factor %.2f GB setup %.1f s' % ($leaf, d['value'], p['local'], p['rhs'], p['solve'], p['step'], d['setup']['levels'], d['setup']['factor_bytes']/1e9, d['setup']['seconds']))"
+done; done
