@@ -9,9 +9,15 @@
 //     backward (levels descending):  x_J  = inv(L_JJ)^T y_J  -  (L_RJ inv(L_JJ))^T x_R
 // Supernodes of one tree level are independent, so a level is ONE kernel launch over all of its tiles.
 // The panels are cut into 64 x 64 tiles stored contiguously in exactly the order they are streamed (a second,
-// transposed copy serves the backward pass, so both passes read memory linearly); one thread owns one output
-// row of a tile, reads its row of the tile with unit stride across the warp and multiplies it into the three
-// right-hand sides held in shared memory.  The kernel is bandwidth bound: 8 B of factor per 3 FMAs.
+// transposed copy serves the backward pass, so both passes read memory linearly).  A CTA fetches its tile with ONE
+// bulk-async copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) issued before griddepcontrol.wait -- the factor
+// does not depend on the vectors, so with programmatic dependent launch the next level's tiles stream in during the
+// tail of the current level -- gathers its slice of the right-hand sides meanwhile, and multiplies from shared memory
+// (k_solve_level_tma).  The kernel is bandwidth bound: 8 B of factor per 3 FMAs.  k_solve_level_pf is the
+// register-streaming fallback, k_solve_level_det the bit-reproducible (atomic-free) variant.  Variants that lost their
+// measurements were removed in round 2 (plain per-level kernel, register-prefetch PDL kernel, persistent ring kernel
+// with grid barriers, ring kernel per level: DESIGN.md 3 keeps the numbers).
+// A mesh partitioned over several ranks shards the solve by subtrees of the elimination tree (shard_owners).
 // Node vectors are in elimination order already (the device node order IS the nested-dissection order), so
 // there is no permutation step around the solve.
 #include <algorithm>
@@ -46,12 +52,7 @@ struct DirectSolver {
 	std::vector<int> fwd_first, fwd_count, bwd_first, bwd_count; // per level, into d_tiles
 	size_t data_doubles = 0;
 	size_t n_tiles = 0;
-	// persistent kernel: phases = forward levels ascending then backward levels descending
-	DevBuf<int> d_phase_first, d_phase_count;
-	DevBuf<int> d_err;
-	int n_phases = 0, grid = 0;
-	int mode = 4;   // 4 (default) = launch per level, tile by bulk-async copy, programmatic dependent launch between levels; 5 = the bulk-copy ring kernel per level + PDL; 3 = launch per level, factor columns requested before the vector gather; 0 = launch per level, gather first;
-	                // 1 = persistent bulk-async kernel; 2 = per level with programmatic dependent launch (1, 2: measured slower, kept selectable)
+	int mode = 4;   // 4 (default) = launch per level, tile by bulk-async copy, programmatic dependent launch between levels; 3 = register-streaming fallback
 	int unroll = 16; // loads in flight per thread of the per-level kernel (ADMMB_SOLVE_UNROLL = 8 | 16 | 32)
 	int slots = 0;   // resident CTAs of the per-level kernel on the whole device
 	int split = 0;   // ADMMB_SOLVE_SPLIT: 0 = choose per level, else log2 of the forced column split + 1
@@ -79,52 +80,9 @@ struct DirectSolver {
 // fire-and-forget FP64 add at L2 (RED.E.ADD.F64): the generic atomicAdd would also emit a shared-memory CAS path
 __device__ __forceinline__ void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(TILE_R) k_solve_level(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
-                                                        const int *__restrict__ pool, double *vb, double *vy, double *vx) {
-	const SolveTile t = tiles[blockIdx.x];
-	__shared__ double sv[TILE_C][3];
-	double *vecs[3] = { vb, vy, vx };
-	const double *vin = vecs[(t.flags >> TF_IN_SHIFT) & 3];
-	double *vout = vecs[(t.flags >> TF_OUT_SHIFT) & 3];
-	for (int c = threadIdx.x; c < t.ncols; c += TILE_R) {
-		const int gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c] : t.in_idx + c;
-		sv[c][0] = vin[3 * (size_t)gi + 0];
-		sv[c][1] = vin[3 * (size_t)gi + 1];
-		sv[c][2] = vin[3 * (size_t)gi + 2];
-	}
-	__syncthreads();
-	const int r = threadIdx.x;
-	if (r >= t.nrows) return;
-	const double *M = data + t.off + r;
-	const int ld = t.nrows;
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-	int c = 0;
-	for (; c + UNROLL <= t.ncols; c += UNROLL) {
-		double m[UNROLL];
-#pragma unroll
-		for (int k = 0; k < UNROLL; ++k) m[k] = __ldcs(M + (size_t)(c + k) * ld); // streaming: the factor is read once per pass
-#pragma unroll
-		for (int k = 0; k < UNROLL; ++k) {
-			a0 += m[k] * sv[c + k][0];
-			a1 += m[k] * sv[c + k][1];
-			a2 += m[k] * sv[c + k][2];
-		}
-	}
-	for (; c < t.ncols; ++c) {
-		const double m = __ldcs(M + (size_t)c * ld);
-		a0 += m * sv[c][0];
-		a1 += m * sv[c][1];
-		a2 += m * sv[c][2];
-	}
-	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
-	const int go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r;
-	red_add(vout + 3 * (size_t)go + 0, a0);
-	red_add(vout + 3 * (size_t)go + 1, a1);
-	red_add(vout + 3 * (size_t)go + 2, a2);
-}
-
-// Variant (ADMMB_SOLVE_MODE=3): the first UNROLL columns of the tile are requested BEFORE the right-hand-side gather.
+// Register-streaming variant (ADMMB_SOLVE_MODE=3; the fallback when the bulk-copy kernel below cannot get its shared
+// memory): one thread per output row of a tile, UNROLL loads in flight per thread; the first UNROLL columns of the tile are
+// requested BEFORE the right-hand-side gather.
 // The factor does not depend on the vectors, so the two latency chains (descriptor -> index -> vector gather, and
 // descriptor -> factor columns) overlap instead of following each other; the small tiles of the lower tree levels are
 // one such chain long, so this is where the time goes there (profiles/r1c_solve.txt: 13 MB levels take 11 us).
@@ -274,70 +232,8 @@ __global__ void __launch_bounds__(TILE_R) k_solve_level_det(const SolveTile *__r
 	v[0] += s0; v[1] += s1; v[2] += s2;
 }
 
-// Same tile product, launched once per level with PROGRAMMATIC DEPENDENT LAUNCH: every CTA first releases the next
-// level's grid (griddepcontrol.launch_dependents) and pulls its whole 64 x 64 tile row into registers (64
-// independent 8-byte loads per thread in flight -- the factor does not depend on the right-hand side), and only
-// then waits for the previous level to complete (griddepcontrol.wait) before it touches the vectors.  The tail of
-// level p therefore overlaps the factor prefetch of level p + 1 instead of draining the machine 28 times a solve.
-__global__ void __launch_bounds__(TILE_R) k_solve_level_pdl(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
-                                                            const int *__restrict__ pool, double *vb, double *vy, double *vx) {
-	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-	const SolveTile t = tiles[blockIdx.x];
-	__shared__ double sv[TILE_C][3];
-	const int r = threadIdx.x;
-	const bool active = r < t.nrows;
-	double m[TILE_C];
-	{
-		const double *M = data + t.off + (active ? r : 0);
-		const int ld = t.nrows;
-#pragma unroll
-		for (int c = 0; c < TILE_C; ++c) m[c] = (active && c < t.ncols) ? __ldcs(M + (size_t)c * ld) : 0.0;
-	}
-	// index lists do not depend on the previous level either
-	int gi_in = 0, go = 0;
-	if (r < t.ncols) gi_in = (t.flags & TF_IN_LIST) ? pool[t.in_idx + r] : t.in_idx + r;
-	if (active) go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r;
-	asm volatile("griddepcontrol.wait;" ::: "memory");
-	double *vecs[3] = { vb, vy, vx };
-	const double *vin = vecs[(t.flags >> TF_IN_SHIFT) & 3];
-	double *vout = vecs[(t.flags >> TF_OUT_SHIFT) & 3];
-	if (r < t.ncols) {
-		sv[r][0] = __ldcg(vin + 3 * (size_t)gi_in + 0);
-		sv[r][1] = __ldcg(vin + 3 * (size_t)gi_in + 1);
-		sv[r][2] = __ldcg(vin + 3 * (size_t)gi_in + 2);
-	}
-	__syncthreads();
-	if (!active) return;
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-	for (int c = 0; c < TILE_C; ++c) {
-		if (c < t.ncols) {
-			a0 += m[c] * sv[c][0];
-			a1 += m[c] * sv[c][1];
-			a2 += m[c] * sv[c][2];
-		}
-	}
-	if (t.flags & TF_NEG) { a0 = -a0; a1 = -a1; a2 = -a2; }
-	red_add(vout + 3 * (size_t)go + 0, a0);
-	red_add(vout + 3 * (size_t)go + 1, a1);
-	red_add(vout + 3 * (size_t)go + 2, a2);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Persistent version of the whole solve: ONE launch, CTAs stay resident (grid = SMs x occupancy) and walk the
-// 2 x levels phases themselves.  Tiles of a phase are dealt round-robin to the CTAs; each CTA streams its tiles
-// through a ring of shared-memory stages filled by bulk-async copies (cp.async.bulk -> UBLKCP, completion on an
-// mbarrier), so the factor keeps flowing while the previous tile is multiplied -- and because the factor does not
-// depend on the right-hand side, the ring keeps prefetching ACROSS phase boundaries; only the small vector reads
-// wait for the grid barrier that separates two tree levels.  This removes the two problems ncu showed for the
-// launch-per-level version (profiles/r1a_solve.txt): every launch was less than one wave and latency bound, and
-// 28 launch gaps per solve.
-// ---------------------------------------------------------------------------------------------------------
-#define PS_THREADS 256           // 4 column groups x 64 rows: a tile is multiplied in 16 steps, not 64
-#define PS_GROUPS (PS_THREADS / TILE_R)
-#define PS_STAGES 3
+// bulk-async copy (cp.async.bulk -> UBLKCP) and mbarrier helpers of the tile kernel below
 #define PS_TILE_BYTES (TILE_R * TILE_C * 8)
-#define PS_SMEM (PS_STAGES * PS_TILE_BYTES + 2 * TILE_C * 3 * 8 + PS_GROUPS * TILE_R * 3 * 8 + PS_STAGES * 8 + 64)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -363,23 +259,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 	    "}\n" ::"r"(smem_u32(bar)),
 	    "r"(parity)
 	    : "memory");
-}
-
-struct TileCursor { int phase, t; }; // t = index inside the phase
-
-// advance to this CTA's next tile (round-robin inside a phase, then the following phases); phase = n_phases at the end
-__device__ __forceinline__ void cursor_next(TileCursor &c, const int *__restrict__ pcount, int n_phases, int cta, int grid) {
-	c.t += grid;
-	while (c.phase < n_phases && c.t >= pcount[c.phase]) { c.phase++; c.t = cta; }
-}
-
-// one element of a tile's right-hand-side slice (thread tid < 3*ncols loads element (c = tid/3, k = tid%3)); L2 read,
-// the values were produced by other CTAs' REDs
-__device__ __forceinline__ double load_rhs_elem(const SolveTile &t, const int *__restrict__ pool, double *const *vecs, int tid) {
-	if (tid >= 3 * t.ncols) return 0.0;
-	const int c = tid / 3, k = tid - 3 * c;
-	const int gi = (t.flags & TF_IN_LIST) ? pool[t.in_idx + c] : t.in_idx + c;
-	return __ldcg(vecs[(t.flags >> TF_IN_SHIFT) & 3] + 3 * (size_t)gi + k);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -461,136 +340,14 @@ __global__ void __launch_bounds__(LT_THREADS) k_solve_level_tma(const SolveTile 
 	}
 }
 
-// PDL = true: launched once PER LEVEL (n_phases = 1, no grid barrier) with programmatic dependent launch between the
-// levels (ADMMB_SOLVE_MODE=5): the ring keeps the factor streaming inside a level -- no bubble between "waves" of
-// one-tile CTAs -- and the first PS_STAGES tiles of a CTA are requested before griddepcontrol.wait, i.e. during the tail
-// of the previous level.
-template <bool PDL>
-__global__ void __launch_bounds__(PS_THREADS) k_solve_persistent(const SolveTile *__restrict__ tiles, const double *__restrict__ data,
-                                                                 const int *__restrict__ pool, const int *__restrict__ pfirst,
-                                                                 const int *__restrict__ pcount, int n_phases, double *vb, double *vy,
-                                                                 double *vx, unsigned *gbar, int *err) {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	double *stage = reinterpret_cast<double *>(smem_raw);                                        // PS_STAGES x 64 x 64
-	double *sv = reinterpret_cast<double *>(smem_raw + PS_STAGES * PS_TILE_BYTES);               // 2 x (TILE_C x 3), double buffered
-	double *part = sv + 2 * TILE_C * 3;                                                          // PS_GROUPS x 64 x 3 partial sums
-	unsigned long long *full = reinterpret_cast<unsigned long long *>(part + PS_GROUPS * TILE_R * 3);
-	const int cta = blockIdx.x, grid = gridDim.x, tid = threadIdx.x;
-	const int row = tid & (TILE_R - 1), grp = tid / TILE_R;
-	double *vecs[3] = { vb, vy, vx };
-
-	if (tid == 0) {
-		for (int s = 0; s < PS_STAGES; ++s) mbar_init(&full[s], 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
-	// producer cursor (thread 0) runs up to PS_STAGES tiles ahead of the consumer cursor
-	TileCursor prod = { 0, cta - grid }, cons = { 0, cta - grid };
-	cursor_next(prod, pcount, n_phases, cta, grid);
-	cursor_next(cons, pcount, n_phases, cta, grid);
-	if (tid == 0) {
-		for (int i = 0; i < PS_STAGES && prod.phase < n_phases; ++i) {
-			const SolveTile t = tiles[pfirst[prod.phase] + prod.t];
-			const unsigned bytes = ((unsigned)(t.nrows * t.ncols * 8) + 15u) & ~15u;
-			mbar_expect_tx(&full[i], bytes);
-			bulk_g2s(stage + (size_t)i * (TILE_R * TILE_C), data + t.off, bytes, &full[i]);
-			cursor_next(prod, pcount, n_phases, cta, grid);
-		}
-	}
-	if (PDL) {
-		asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-		asm volatile("griddepcontrol.wait;" ::: "memory"); // the vectors of the previous level are complete and visible
-	}
-	int consumed = 0, svbuf = 0;
-	for (int phase = 0; phase < n_phases; ++phase) {
-		if (phase > 0) {
-			// grid barrier: every CTA has finished (and made visible) its outputs of phase - 1
-			if (tid == 0) {
-				unsigned spins = 0;
-				while (*((volatile unsigned *)&gbar[phase - 1]) < (unsigned)grid) {
-					if (++spins > 400000000u) { *err = 1; break; }
-				}
-				__threadfence();
-			}
-			__syncthreads();
-		}
-		bool have_sv = false; // the first tile of a phase reads its right-hand side after the barrier
-		while (cons.phase == phase) {
-			const int s = consumed % PS_STAGES;
-			const SolveTile t = tiles[pfirst[phase] + cons.t];
-			if (!have_sv) {
-				const double v = load_rhs_elem(t, pool, vecs, tid);
-				if (tid < 3 * TILE_C) sv[svbuf * (TILE_C * 3) + tid] = v;
-			}
-			// prefetch the NEXT tile's right-hand side into a register while this tile is multiplied (same phase only)
-			TileCursor nxt = cons;
-			cursor_next(nxt, pcount, n_phases, cta, grid);
-			const bool nxt_same = (nxt.phase == phase);
-			SolveTile tn = t;
-			double vnext = 0.0;
-			if (nxt_same) { tn = tiles[pfirst[phase] + nxt.t]; vnext = load_rhs_elem(tn, pool, vecs, tid); }
-			mbar_wait(&full[s], (unsigned)((consumed / PS_STAGES) & 1));
-			__syncthreads();
-			{
-				// thread (row, grp): columns grp, grp + 4, ... of the tile -> partial sums
-				const double *M = stage + (size_t)s * (TILE_R * TILE_C) + row;
-				const double *v = sv + svbuf * (TILE_C * 3);
-				const int ld = t.nrows;
-				double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-				if (row < t.nrows) {
-#pragma unroll 4
-					for (int c = grp; c < t.ncols; c += PS_GROUPS) {
-						const double m = M[c * ld];
-						a0 += m * v[3 * c + 0];
-						a1 += m * v[3 * c + 1];
-						a2 += m * v[3 * c + 2];
-					}
-				}
-				part[(grp * TILE_R + row) * 3 + 0] = a0;
-				part[(grp * TILE_R + row) * 3 + 1] = a1;
-				part[(grp * TILE_R + row) * 3 + 2] = a2;
-			}
-			__syncthreads(); // partial sums complete; stage s and sv[svbuf] are free again
-			if (tid == 0 && prod.phase < n_phases) {
-				const SolveTile tp = tiles[pfirst[prod.phase] + prod.t];
-				const unsigned bytes = ((unsigned)(tp.nrows * tp.ncols * 8) + 15u) & ~15u;
-				mbar_expect_tx(&full[s], bytes);
-				bulk_g2s(stage + (size_t)s * (TILE_R * TILE_C), data + tp.off, bytes, &full[s]);
-				cursor_next(prod, pcount, n_phases, cta, grid);
-			}
-			if (tid < 3 * t.nrows) {
-				// thread tid adds the four partials of output element (r = tid/3, k = tid%3) and sends one RED
-				const int r = tid / 3, k = tid - 3 * r;
-				double a = (part[(0 * TILE_R + r) * 3 + k] + part[(1 * TILE_R + r) * 3 + k]) + (part[(2 * TILE_R + r) * 3 + k] + part[(3 * TILE_R + r) * 3 + k]);
-				if (t.flags & TF_NEG) a = -a;
-				const int go = (t.flags & TF_OUT_LIST) ? pool[t.out_idx + r] : t.out_idx + r;
-				red_add(vecs[(t.flags >> TF_OUT_SHIFT) & 3] + 3 * (size_t)go + k, a);
-			}
-			svbuf ^= 1;
-			if (nxt_same && tid < 3 * TILE_C) sv[svbuf * (TILE_C * 3) + tid] = vnext;
-			have_sv = nxt_same;
-			++consumed;
-			cons = nxt;
-			// (the next iteration's first __syncthreads orders these smem writes before they are read, and the reads of
-			// `part` above before the next tile overwrites it)
-		}
-		// arrive at the barrier of this phase
-		__threadfence();
-		__syncthreads();
-		if (tid == 0 && phase + 1 < n_phases) atomicAdd(&gbar[phase], 1u);
-	}
-}
-
 void direct_set_blocks(admmb_ctx *ctx, const std::vector<int> &block_end) {
 	if (!ctx->direct) ctx->direct = new DirectSolver();
 	ctx->direct->block_end = block_end;
 }
 
-// y of the direct solve, for the right-hand-side kernel to clear (false: no direct solver set up, or the persistent
-// variant whose barrier counters sit behind y and need the memset)
+// y of the direct solve, for the right-hand-side kernel to clear (false: no direct solver set up)
 bool direct_vectors(admmb_ctx *ctx, double **y) {
-	if (!ctx->direct || !ctx->direct->d_y.p || ctx->direct->mode == 1) return false;
+	if (!ctx->direct || !ctx->direct->d_y.p) return false;
 	*y = ctx->direct->d_y.p;
 	return true;
 }
@@ -911,38 +668,19 @@ int direct_setup(admmb_ctx *ctx) {
 		if (verbose) fprintf(stderr, "[setup] rank %d: sharded solve, %.1f %% of the factor replicated, %zu + %zu own / top forward levels, %d top rows\n",
 		                     ctx->dist_rank, 100.0 * S.top_fraction, S.sh_sub_fwd.size(), S.sh_top_fwd.size(), S.n_top_rows);
 	}
-	// persistent kernel schedule: forward levels ascending, then backward levels descending
+	// solve variant and its launch parameters
 	{
-		std::vector<int> pf, pc;
-		for (int lv = 0; lv < F.nlevels; ++lv) { pf.push_back(S.fwd_first[lv]); pc.push_back(S.fwd_count[lv]); }
-		for (int lv = F.nlevels - 1; lv >= 0; --lv) { pf.push_back(S.bwd_first[lv]); pc.push_back(S.bwd_count[lv]); }
-		S.n_phases = (int)pf.size();
-		ADMMB_CUDA(ctx, S.d_phase_first.upload(pf, s));
-		ADMMB_CUDA(ctx, S.d_phase_count.upload(pc, s));
-		ADMMB_CUDA(ctx, S.d_err.alloc(1));
-		ADMMB_CUDA(ctx, S.d_err.zero(s));
-		// y plus the per-phase barrier counters live in one allocation so that one memset clears both
-		ADMMB_CUDA(ctx, S.d_y.alloc(3 * (size_t)ctx->n + (size_t)(S.n_phases + 2) / 2 + 2));
-		const int smem = PS_SMEM;
-		ADMMB_CUDA(ctx, cudaFuncSetAttribute(k_solve_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-		int occ = 0, sms = 0;
-		ADMMB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_persistent<false>, PS_THREADS, smem));
+		ADMMB_CUDA(ctx, S.d_y.alloc(3 * (size_t)ctx->n));
+		int sms = 0;
 		ADMMB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-		S.grid = sms * (occ < 1 ? 1 : occ);
 		{
 			const char *e = getenv("ADMMB_SOLVE_MODE");
 			S.mode = 4;
-			if (e && e[0] >= '0' && e[0] <= '5') S.mode = e[0] - '0';
-			if (cudaFuncSetAttribute(k_solve_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-				cudaGetLastError();
-				if (S.mode == 5) S.mode = 3;
-			}
-			if (S.mode == 5 && occ < 1) S.mode = 3;
+			if (e && (e[0] == '3' || e[0] == '4')) S.mode = e[0] - '0';
 			if (cudaFuncSetAttribute(k_solve_level_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LT_SMEM) != cudaSuccess) {
 				cudaGetLastError();
-				if (S.mode == 4) S.mode = 3;
+				S.mode = 3;
 			}
-			if (S.mode == 1 && occ < 1) S.mode = 0;
 			if (S.sharded && S.mode != 4) ADMMB_FAIL(ctx, ADMMB_E_STATE, "the sharded solve of a partitioned mesh needs solve mode 4 (ADMMB_DIST_SOLVE=replicated selects the replicated solve)");
 			const char *u = getenv("ADMMB_SOLVE_UNROLL");
 			if (u) { const int v = atoi(u); if (v == 8 || v == 16 || v == 32) S.unroll = v; }
@@ -967,20 +705,11 @@ int direct_solve(admmb_ctx *ctx) {
 	DirectSolver &S = *ctx->direct;
 	cudaStream_t s = ctx->stream;
 	const size_t bytes = 3 * (size_t)ctx->n * sizeof(double);
-	const bool zeroed = ctx->solve_vectors_zeroed && S.mode != 1; // (mode 1 keeps its barrier counters behind y: always memset)
+	const bool zeroed = ctx->solve_vectors_zeroed;
 	ctx->solve_vectors_zeroed = false;
 	if (!zeroed) {
-		ADMMB_CUDA(ctx, cudaMemsetAsync(S.d_y.p, 0, S.d_y.bytes(), s)); // y and the phase barrier counters behind it
+		ADMMB_CUDA(ctx, cudaMemsetAsync(S.d_y.p, 0, S.d_y.bytes(), s));
 		ADMMB_CUDA(ctx, cudaMemsetAsync(ctx->d_currx.p, 0, bytes, s));
-	}
-	if (S.mode == 1 && !S.det) {
-		const int smem = PS_SMEM;
-		unsigned *gbar = reinterpret_cast<unsigned *>(S.d_y.p + 3 * (size_t)ctx->n);
-		k_solve_persistent<false><<<S.grid, PS_THREADS, smem, s>>>(S.d_tiles.p, S.d_data.p, S.d_pool.p, S.d_phase_first.p, S.d_phase_count.p,
-		                                                    S.n_phases, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, gbar, S.d_err.p);
-		ctx->launches++;
-		ADMMB_CUDA(ctx, cudaGetLastError());
-		return ADMMB_OK;
 	}
 	const int nl = S.F.nlevels;
 	if (S.sharded) {
@@ -1041,48 +770,6 @@ int direct_solve(admmb_ctx *ctx) {
 		}
 		return ADMMB_OK;
 	}
-	if (S.mode == 5 && !S.det) {
-		// launch per level: resident CTAs stream the level's tiles through their bulk-copy ring; levels chained by PDL
-		bool first = true;
-		for (int ph = 0; ph < 2 * nl; ++ph) {
-			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
-			const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
-			if (cnt == 0) continue;
-			cudaLaunchConfig_t cfg = {};
-			cfg.gridDim = dim3(std::min(cnt, S.grid)); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = PS_SMEM; cfg.stream = s;
-			cudaLaunchAttribute attr[1];
-			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-			attr[0].val.programmaticStreamSerializationAllowed = 1;
-			cfg.attrs = attr; cfg.numAttrs = (first || S.no_pdl) ? 0 : 1;
-			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_persistent<true>, (const SolveTile *)S.d_tiles.p, (const double *)S.d_data.p,
-			                                   (const int *)S.d_pool.p, (const int *)(S.d_phase_first.p + ph), (const int *)(S.d_phase_count.p + ph), 1,
-			                                   ctx->d_b.p, S.d_y.p, ctx->d_currx.p, (unsigned *)nullptr, S.d_err.p));
-			ctx->launches++;
-			first = false;
-		}
-		return ADMMB_OK;
-	}
-	if (S.mode == 2 && !S.det) {
-		// launch per level, each launch (after the first) programmatically dependent on the previous one
-		bool first = true;
-		for (int ph = 0; ph < 2 * nl; ++ph) {
-			const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
-			const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
-			const int off = ph < nl ? S.fwd_first[lv] : S.bwd_first[lv];
-			if (cnt == 0) continue;
-			cudaLaunchConfig_t cfg = {};
-			cfg.gridDim = dim3(cnt); cfg.blockDim = dim3(TILE_R); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-			cudaLaunchAttribute attr[1];
-			attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-			attr[0].val.programmaticStreamSerializationAllowed = 1;
-			cfg.attrs = attr; cfg.numAttrs = first ? 0 : 1;
-			ADMMB_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_solve_level_pdl, (const SolveTile *)(S.d_tiles.p + off), (const double *)S.d_data.p,
-			                                   (const int *)S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p));
-			ctx->launches++;
-			first = false;
-		}
-		return ADMMB_OK;
-	}
 	for (int ph = 0; ph < 2 * nl; ++ph) {
 		const int lv = ph < nl ? ph : 2 * nl - 1 - ph;
 		const int cnt = ph < nl ? S.fwd_count[lv] : S.bwd_count[lv];
@@ -1097,8 +784,9 @@ int direct_solve(admmb_ctx *ctx) {
 			ctx->launches++;
 			continue;
 		}
-		if (S.mode == 3) {
-			// column split: as long as twice the CTAs still fit the machine at once, halve the columns per CTA
+		{
+			// register-streaming fallback (mode 3).  Column split: as long as twice the CTAs still fit the machine at once,
+			// halve the columns per CTA
 			int sl = 0;
 			if (S.split > 0) sl = S.split - 1;
 			else while (sl < 2 && (long)cnt * (2 << sl) <= (long)S.slots) ++sl;
@@ -1106,9 +794,7 @@ int direct_solve(admmb_ctx *ctx) {
 			if (S.unroll == 32) k_solve_level_pf<32><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
 			else if (S.unroll == 16) k_solve_level_pf<16><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
 			else k_solve_level_pf<8><<<g, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p, sl);
-		} else if (S.unroll == 32) k_solve_level<32><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
-		else if (S.unroll == 16) k_solve_level<16><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
-		else k_solve_level<8><<<cnt, TILE_R, 0, s>>>(tl, S.d_data.p, S.d_pool.p, ctx->d_b.p, S.d_y.p, ctx->d_currx.p);
+		}
 		ctx->launches++;
 	}
 	ADMMB_CUDA(ctx, cudaGetLastError());
@@ -1118,7 +804,7 @@ int direct_solve(admmb_ctx *ctx) {
 void direct_destroy(admmb_ctx *ctx) {
 	if (!ctx->direct) return;
 	DirectSolver &S = *ctx->direct;
-	S.d_data.free(); S.d_tiles.free(); S.d_pool.free(); S.d_y.free(); S.d_phase_first.free(); S.d_phase_count.free(); S.d_err.free();
+	S.d_data.free(); S.d_tiles.free(); S.d_pool.free(); S.d_y.free();
 	S.d_top_rows.free(); S.d_top_buf.free();
 	S.d_part.free(); S.d_red_key.free(); S.d_red_ptr.free(); S.d_red_slot.free(); S.d_red_tgt.free(); S.d_red_counter.free();
 	delete ctx->direct;
