@@ -159,25 +159,39 @@ int launch_rhs(admmb_ctx *ctx) {
 }
 
 // =====================================================================================================
-// Jacobi-preconditioned conjugate gradients on A_n with three right-hand sides (x, y, z columns) sharing
-// every matrix read.  Warm-started from the previous ADMM iterate already in curr_x.
+// Jacobi-preconditioned conjugate gradients on A_n with three right-hand sides (x, y, z columns) sharing every matrix
+// read, warm-started from the previous ADMM iterate already in curr_x.  Single-reduction (Chronopoulos-Gear) form:
+//     u = Dinv r,  w = A u,  gamma = r.u,  delta = w.u                      (ONE fused reduction per iteration)
+//     beta = gamma / gamma_old,  alpha = gamma / (delta - beta gamma / alpha_old)
+//     p = u + beta p,  s = w + beta s,  x += alpha p,  r -= alpha s
+// i.e. two kernels per iteration (vector update; SpMV + the nine dot products) instead of three, and on a mesh partitioned
+// over ranks one all-gather of u (the halo exchange in its simplest form) + ONE all-reduce of nine doubles instead of
+// one all-gather + two all-reduces.  The iterations run as CUDA-graph chunks of PCG_CHUNK iterations with a device-side
+// "done" flag (kernels of a finished solve return at once); the host looks at the flag once per batch of chunks, sized
+// from the previous solve's iteration count, so a solve normally costs one host synchronisation.
 // =====================================================================================================
 struct PcgSolver {
 	DevBuf<int> ptr, idx;
 	DevBuf<double> val, dinv;
-	DevBuf<double> r, p, Ap;
-	DevBuf<double> scal; // [0..5] pAp[2][3]; parity q: rz[3] at 6+6q, rr[3] at 9+6q (adjacent: one all-reduce); [18..20] bb[3]; [21] best rr
+	DevBuf<double> r, u, w, p, s;
+	DevBuf<double> scal; // see S_* below
 	DevBuf<int> flag;    // [0] done, [1] iterations used, [2] iterations without progress
 	int *h_flag = nullptr;
 	int grid = 0;
+	cudaGraphExec_t chunk_exec = nullptr;
+	bool graph_failed = false;
+	int last_iters = 0;
 };
 
 #define PCG_THREADS 256
-#define S_PAP(q) (3 * (q))
-#define S_RZ(q) (6 + 6 * (q))
-#define S_RR(q) (9 + 6 * (q))
-#define S_BB 18
-#define S_BEST 21
+#define PCG_CHUNK 16
+// scal: [0..8] gamma, delta, rr of parity 0; [9..11] b.b; [12..20] the same dots of parity 1; [21..26] alpha_old, gamma_old
+// read by parity 0 (written by parity 1); [27..32] the same read by parity 1; [33] best residual seen (stagnation guard)
+#define S_DOTS(q) (12 * (q))
+#define S_BB 9
+#define S_STATE(q) (21 + 6 * (q))
+#define S_BEST 33
+#define S_SIZE 40
 
 __device__ __forceinline__ void block_reduce3_atomic(double a0, double a1, double a2, double *dst) {
 	__shared__ double sh[3][PCG_THREADS / 32];
@@ -203,13 +217,14 @@ __device__ __forceinline__ void block_reduce3_atomic(double a0, double a1, doubl
 	__syncthreads();
 }
 
-// r = b - A x; p = Dinv r; rz[0] = r.p; rr[0] = r.r; bb = b.b
+// r = b - A x; u = Dinv r; p = s = 0; bb = b.b; resets the scalars and the flags (rows [r0, n) of this rank; ptr / dinv are
+// indexed by the local row i - r0, everything else by the global node)
 __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const int *__restrict__ ptr, const int *__restrict__ idx,
                                                           const double *__restrict__ val, const double *__restrict__ dinv,
                                                           const double *__restrict__ b, const double *__restrict__ x,
-                                                          double *__restrict__ r, double *__restrict__ p, double *scal) {
-	// rows [r0, n) of this rank; ptr / dinv are indexed by the local row (i - r0), everything else by the global node
-	double rz[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 }, bb[3] = { 0, 0, 0 };
+                                                          double *__restrict__ r, double *__restrict__ u, double *__restrict__ p,
+                                                          double *__restrict__ s, double *scal, int *flag) {
+	double bb[3] = { 0, 0, 0 };
 	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
 		for (int q = ptr[i - r0]; q < ptr[i - r0 + 1]; ++q) {
@@ -219,109 +234,95 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const i
 		}
 		const double di = dinv[i - r0];
 		for (int j = 0; j < 3; ++j) {
-			const double bj = b[3 * (size_t)i + j];
+			const size_t t = 3 * (size_t)i + j;
+			const double bj = b[t];
 			const double rj = bj - a[j];
-			r[3 * (size_t)i + j] = rj;
-			const double zj = di * rj;
-			p[3 * (size_t)i + j] = zj;
-			rz[j] += rj * zj; rr[j] += rj * rj; bb[j] += bj * bj;
+			r[t] = rj;
+			u[t] = di * rj;
+			p[t] = 0.0;
+			s[t] = 0.0;
+			bb[j] += bj * bj;
 		}
 	}
-	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + S_RZ(0));
-	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_RR(0));
 	block_reduce3_atomic(bb[0], bb[1], bb[2], scal + S_BB);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (int j = 0; j < 3; ++j) { scal[S_STATE(0) + j] = 1.0; scal[S_STATE(0) + 3 + j] = __longlong_as_double(0x7ff0000000000000LL); } // alpha_old = 1, gamma_old = inf: beta = 0, alpha = gamma / delta
+		flag[0] = 0; flag[1] = 0; flag[2] = 0;
+	}
 }
 
-__global__ void k_pcg_check0(double *scal, int *flag, double tol2) {
-	// converged before the first iteration?
-	bool done = true;
-	for (int j = 0; j < 3; ++j) done = done && (scal[S_RR(0) + j] <= tol2 * scal[S_BB + j]);
-	flag[0] = done ? 1 : 0;
-	flag[1] = 0;
-	flag[2] = 0;
-}
-
-// Ap = A p; pAp[k&1] += p.Ap; zero the accumulators the rest of this iteration adds into
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int k, const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                          const double *__restrict__ val, const double *__restrict__ p,
-                                                          double *__restrict__ Ap, double *scal, const int *flag) {
+// w = A u; dots[q] += (r.u, w.u, r.r)
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int q, const int *__restrict__ ptr, const int *__restrict__ idx,
+                                                          const double *__restrict__ val, const double *__restrict__ u,
+                                                          const double *__restrict__ r, double *__restrict__ w, double *scal, const int *flag) {
 	if (flag[0]) return;
-	const int cur = k & 1, nxt = cur ^ 1;
-	double s[3] = { 0, 0, 0 };
+	double g[3] = { 0, 0, 0 }, d[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 };
 	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
-		for (int q = ptr[i - r0]; q < ptr[i - r0 + 1]; ++q) {
-			const double av = val[q];
-			const double *pc = p + 3 * (size_t)idx[q];
-			a[0] += av * pc[0]; a[1] += av * pc[1]; a[2] += av * pc[2];
+		for (int e = ptr[i - r0]; e < ptr[i - r0 + 1]; ++e) {
+			const double av = val[e];
+			const double *uc = u + 3 * (size_t)idx[e];
+			a[0] += av * uc[0]; a[1] += av * uc[1]; a[2] += av * uc[2];
 		}
-		for (int j = 0; j < 3; ++j) { Ap[3 * (size_t)i + j] = a[j]; s[j] += a[j] * p[3 * (size_t)i + j]; }
+		for (int j = 0; j < 3; ++j) {
+			const size_t t = 3 * (size_t)i + j;
+			const double rj = r[t], uj = u[t];
+			w[t] = a[j];
+			g[j] += rj * uj; d[j] += a[j] * uj; rr[j] += rj * rj;
+		}
 	}
-	if (blockIdx.x == 0 && threadIdx.x < 3) { scal[S_RZ(nxt) + threadIdx.x] = 0.0; scal[S_RR(nxt) + threadIdx.x] = 0.0; }
-	block_reduce3_atomic(s[0], s[1], s[2], scal + S_PAP(cur));
+	block_reduce3_atomic(g[0], g[1], g[2], scal + S_DOTS(q) + 0);
+	block_reduce3_atomic(d[0], d[1], d[2], scal + S_DOTS(q) + 3);
+	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_DOTS(q) + 6);
 }
 
-// alpha = rz/pAp; x += alpha p; r -= alpha Ap; rz[nxt] += r.Dinv r; rr[nxt] += r.r
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int k, const double *__restrict__ dinv, const double *__restrict__ p,
-                                                            const double *__restrict__ Ap, double *__restrict__ x,
-                                                            double *__restrict__ r, double *scal, const int *flag) {
+// convergence test on dots[q]; beta, alpha; p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = Dinv r
+__global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int q, const double *__restrict__ dinv, double *__restrict__ u,
+                                                            const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
+                                                            double *__restrict__ x, double *__restrict__ r, double *scal, int *flag, double tol2) {
 	if (flag[0]) return;
-	const int cur = k & 1, nxt = cur ^ 1;
-	double alpha[3];
+	const int nq = q ^ 1;
+	double alpha[3], beta[3], gamma[3], rrs = 0.0;
+	bool done = true;
 	for (int j = 0; j < 3; ++j) {
-		const double pAp = scal[S_PAP(cur) + j];
-		alpha[j] = (pAp > 0.0) ? scal[S_RZ(cur) + j] / pAp : 0.0;
+		gamma[j] = scal[S_DOTS(q) + j];
+		const double delta = scal[S_DOTS(q) + 3 + j], rr = scal[S_DOTS(q) + 6 + j];
+		const double a_old = scal[S_STATE(q) + j], g_old = scal[S_STATE(q) + 3 + j];
+		done = done && (rr <= tol2 * scal[S_BB + j]);
+		rrs += rr;
+		beta[j] = (g_old > 0.0) ? gamma[j] / g_old : 0.0;
+		const double den = delta - beta[j] * gamma[j] / a_old;
+		alpha[j] = (den > 0.0) ? gamma[j] / den : 0.0;   // breakdown (rounding-level residual): no step in this column
 	}
-	double rz[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 };
+	if (done) {
+		if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) flag[0] = 1;
+		return;
+	}
 	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const double di = dinv[i - r0];
 		for (int j = 0; j < 3; ++j) {
 			const size_t t = 3 * (size_t)i + j;
-			x[t] += alpha[j] * p[t];
-			const double rj = r[t] - alpha[j] * Ap[t];
+			const double pj = u[t] + beta[j] * p[t];
+			const double sj = w[t] + beta[j] * s[t];
+			p[t] = pj; s[t] = sj;
+			x[t] += alpha[j] * pj;
+			const double rj = r[t] - alpha[j] * sj;
 			r[t] = rj;
-			rz[j] += rj * (di * rj); rr[j] += rj * rj;
+			u[t] = di * rj;
 		}
 	}
-	block_reduce3_atomic(rz[0], rz[1], rz[2], scal + S_RZ(nxt));
-	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_RR(nxt));
-}
-
-// beta = rz_new/rz_old; p = Dinv r + beta p; convergence test; zero pAp for the next iteration
-__global__ void __launch_bounds__(PCG_THREADS) k_pcg_direction(int r0, int n, int k, const double *__restrict__ dinv, const double *__restrict__ r,
-                                                               double *__restrict__ p, double *scal, int *flag, double tol2) {
-	if (flag[0]) return;
-	const int cur = k & 1, nxt = cur ^ 1;
-	double beta[3];
-	bool done = true;
-	for (int j = 0; j < 3; ++j) {
-		const double o = scal[S_RZ(cur) + j];
-		beta[j] = (o > 0.0) ? scal[S_RZ(nxt) + j] / o : 0.0;
-		done = done && (scal[S_RR(nxt) + j] <= tol2 * scal[S_BB + j]);
-	}
-	if (!done) {
-		for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-			const double di = dinv[i - r0];
-			for (int j = 0; j < 3; ++j) {
-				const size_t t = 3 * (size_t)i + j;
-				p[t] = di * r[t] + beta[j] * p[t];
-			}
-		}
-	}
-	// All blocks have read scal[*cur*] above only through registers; the writes below touch slots that no
-	// block of THIS kernel reads (pAp[nxt]) or that are only read by later kernels (flag).
+	if (blockIdx.x == 0 && threadIdx.x < 9) scal[S_DOTS(nq) + threadIdx.x] = 0.0; // the SpMV of this iteration accumulates here
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		scal[S_PAP(nxt) + 0] = 0.0; scal[S_PAP(nxt) + 1] = 0.0; scal[S_PAP(nxt) + 2] = 0.0;
+		for (int j = 0; j < 3; ++j) { scal[S_STATE(nq) + j] = alpha[j]; scal[S_STATE(nq) + 3 + j] = gamma[j]; }
+		const int k = flag[1];
 		flag[1] = k + 1;
-		// stagnation guard: once the residual sits at rounding level CG must not be iterated further (the recurrences
-		// break down: p.Ap underflows and the iterate blows up).  The residual 2-norm of CG is NOT monotone -- on the
-		// 1 M-tet cube it rises for dozens of iterations after a large step -- so the window is long: 300 iterations
-		// without a 1 % improvement of the best residual seen.  A NaN stops at once.
-		const double rr = scal[S_RR(nxt)] + scal[S_RR(nxt) + 1] + scal[S_RR(nxt) + 2];
-		if (k == 0 || rr < 0.99 * scal[S_BEST]) { scal[S_BEST] = rr; flag[2] = 0; }
-		else if (++flag[2] >= 300 || !(rr == rr)) flag[0] = 1;
+		// stagnation guard: once the residual sits at rounding level CG must not be iterated further (the recurrences break
+		// down and the iterate blows up).  The residual 2-norm of CG is NOT monotone -- on the 1 M-tet cube it rises for
+		// dozens of iterations after a large step -- so the window is long: 300 iterations without a 1 % improvement of the
+		// best residual seen.  A NaN stops at once.
+		if (k == 0 || rrs < 0.99 * scal[S_BEST]) { scal[S_BEST] = rrs; flag[2] = 0; }
+		else if (++flag[2] >= 300 || !(rrs == rrs)) flag[0] = 1;
 	}
-	if (done && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) flag[0] = 1;
 }
 
 int pcg_setup(admmb_ctx *ctx) {
@@ -349,18 +350,34 @@ int pcg_setup(admmb_ctx *ctx) {
 	ADMMB_CUDA(ctx, S.val.upload(val, ctx->stream));
 	ADMMB_CUDA(ctx, S.dinv.upload(dinv, ctx->stream));
 	ADMMB_CUDA(ctx, S.r.alloc(npad));
+	ADMMB_CUDA(ctx, S.u.alloc(npad));
+	ADMMB_CUDA(ctx, S.w.alloc(npad));
 	ADMMB_CUDA(ctx, S.p.alloc(npad));
-	ADMMB_CUDA(ctx, S.Ap.alloc(npad));
-	ADMMB_CUDA(ctx, S.p.zero(ctx->stream));
-	ADMMB_CUDA(ctx, S.scal.alloc(24));
+	ADMMB_CUDA(ctx, S.s.alloc(npad));
+	ADMMB_CUDA(ctx, S.u.zero(ctx->stream));
+	ADMMB_CUDA(ctx, S.scal.alloc(S_SIZE));
 	ADMMB_CUDA(ctx, S.flag.alloc(4));
 	if (!S.h_flag) ADMMB_CUDA(ctx, cudaMallocHost((void **)&S.h_flag, 2 * sizeof(int)));
+	if (S.chunk_exec) { cudaGraphExecDestroy(S.chunk_exec); S.chunk_exec = nullptr; }
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 	const int want = (r1 - r0 + PCG_THREADS - 1) / PCG_THREADS;
 	S.grid = want < sms * 4 ? (want > 0 ? want : 1) : sms * 4;
 	(void)n;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ADMMB_OK;
+}
+
+// one CG iteration entering with the dots of parity q complete
+static int pcg_enqueue_iteration(admmb_ctx *ctx, PcgSolver &S, int q, double tol2) {
+	const int r0 = ctx->own0, r1 = ctx->own1;
+	cudaStream_t s = ctx->stream;
+	int rc;
+	k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q, S.dinv.p, S.u.p, S.w.p, S.p.p, S.s.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p, tol2);
+	if ((rc = dist_allgather_nodes(ctx, S.u.p))) return rc;
+	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q ^ 1, S.ptr.p, S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p);
+	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(q ^ 1), 9))) return rc;
+	ctx->launches += 2;
 	return ADMMB_OK;
 }
 
@@ -372,28 +389,41 @@ int pcg_solve(admmb_ctx *ctx) {
 	const double tol2 = tol * tol;
 	int rc;
 	ADMMB_CUDA(ctx, S.scal.zero(s));
-	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.p.p, S.scal.p);
-	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_RZ(0), 15))) return rc; // rz[0], rr[0], (rz[1], rr[1] still zero), bb
-	if ((rc = dist_allgather_nodes(ctx, S.p.p))) return rc;
-	k_pcg_check0<<<1, 1, 0, s>>>(S.scal.p, S.flag.p, tol2);
+	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.u.p, S.p.p, S.s.p, S.scal.p, S.flag.p);
+	if ((rc = dist_allgather_nodes(ctx, S.u.p))) return rc;
+	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, 0, S.ptr.p, S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p);
+	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(0), 12))) return rc; // the dots of parity 0 and b.b
 	ctx->launches += 2;
-	const int chunk = 32;
+	// chunk of PCG_CHUNK iterations (even: the parities repeat), captured once
+	if (!S.chunk_exec && !S.graph_failed && ctx->use_graph) {
+		cudaGraph_t g = nullptr;
+		const long before = ctx->launches;
+		cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+		rc = ADMMB_OK;
+		if (e == cudaSuccess) {
+			for (int c = 0; c < PCG_CHUNK && !rc; ++c) rc = pcg_enqueue_iteration(ctx, S, c & 1, tol2);
+			e = cudaStreamEndCapture(s, &g);
+		}
+		if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&S.chunk_exec, g, 0);
+		if (g) cudaGraphDestroy(g);
+		ctx->launches = before;
+		if (e != cudaSuccess || rc) { S.chunk_exec = nullptr; S.graph_failed = true; cudaGetLastError(); }
+	}
 	int k = 0;
+	// chunks enqueued before the host looks at the flag: enough for the previous solve's iteration count
+	int batch = std::max(1, (S.last_iters + PCG_CHUNK - 1) / PCG_CHUNK);
+	S.h_flag[0] = 0; S.h_flag[1] = 0;
 	while (k < ctx->cg_max_iters) {
-		for (int c = 0; c < chunk && k < ctx->cg_max_iters; ++c, ++k) {
-			const int cur = k & 1, nxt = cur ^ 1;
-			k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.ptr.p, S.idx.p, S.val.p, S.p.p, S.Ap.p, S.scal.p, S.flag.p);
-			if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_PAP(cur), 3))) return rc;
-			k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.dinv.p, S.p.p, S.Ap.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p);
-			if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_RZ(nxt), 6))) return rc;
-			k_pcg_direction<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, k, S.dinv.p, S.r.p, S.p.p, S.scal.p, S.flag.p, tol2);
-			if ((rc = dist_allgather_nodes(ctx, S.p.p))) return rc;
-			ctx->launches += 3;
+		for (int c = 0; c < batch && k < ctx->cg_max_iters; ++c, k += PCG_CHUNK) {
+			if (S.chunk_exec) { ADMMB_CUDA(ctx, cudaGraphLaunch(S.chunk_exec, s)); ctx->launches += 2 * PCG_CHUNK; }
+			else for (int i = 0; i < PCG_CHUNK; ++i) if ((rc = pcg_enqueue_iteration(ctx, S, i & 1, tol2))) return rc;
 		}
 		ADMMB_CUDA(ctx, cudaMemcpyAsync(S.h_flag, S.flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
 		if (S.h_flag[0]) break;
+		batch = 1;
 	}
+	S.last_iters = S.h_flag[1];
 	ctx->cg_iters_total += S.h_flag[1];
 	// every rank needs the whole iterate for the next local step
 	if ((rc = dist_allgather_nodes(ctx, ctx->d_currx.p))) return rc;
@@ -404,7 +434,8 @@ int pcg_solve(admmb_ctx *ctx) {
 void pcg_destroy(admmb_ctx *ctx) {
 	if (!ctx->pcg) return;
 	PcgSolver &S = *ctx->pcg;
-	S.ptr.free(); S.idx.free(); S.val.free(); S.dinv.free(); S.r.free(); S.p.free(); S.Ap.free(); S.scal.free(); S.flag.free();
+	S.ptr.free(); S.idx.free(); S.val.free(); S.dinv.free(); S.r.free(); S.u.free(); S.w.free(); S.p.free(); S.s.free(); S.scal.free(); S.flag.free();
+	if (S.chunk_exec) cudaGraphExecDestroy(S.chunk_exec);
 	if (S.h_flag) cudaFreeHost(S.h_flag);
 	delete ctx->pcg;
 	ctx->pcg = nullptr;
