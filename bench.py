@@ -457,6 +457,7 @@ def main():
         sim.step_resident(frames=max(args.warmup, 3))
         barrier()
         l0 = sim.info()["launches_total"]
+        cg0 = sim.info()["cg_iters_total"]
         if sampler:
             sampler.begin()
         if args.profile_region:
@@ -468,6 +469,7 @@ def main():
             sampler.end()
         ms = sim.last_region_ms()
         l1 = sim.info()["launches_total"]
+        timed_resident.cg_per_iteration = (sim.info()["cg_iters_total"] - cg0) / float(args.steps * iters_per_frame)
         barrier()
         return ms, l1 - l0
 
@@ -479,6 +481,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_region, launches = timed_resident(sim, sampler)
+    cg_per_iteration = timed_resident.cg_per_iteration
     clocks = sampler.stop()
     # per-phase split, same regime (the optimiser reached its steady state in the conditioning frames): CUDA events around
     # the three phases of every iteration, as many frames as the timed region
@@ -554,6 +557,7 @@ def main():
             "config": {"workload": label + f"; solver={args.solver}",
                        "conditioning": f"{CONDITION_FRAMES} untimed frames before the --warmup frames on every arm (the reference's line search needs ~20 frames to reach "
                                        "its steady regime: maxfev evaluations in almost every tet)",
+                       "cg_iterations_per_admm_iteration": cg_per_iteration if args.solver == "pcg" else None,
                        "parallelism": f"ensemble x{world} (one scene per GPU, no collective); the single mesh partitioned over the same GPUs is `partition`" if world > 1 else "single GPU",
                        "l2": "working set (factor %.2f GB + force arrays %.2f GB) exceeds the 126 MB L2, no flush needed" % (
                            info0["factor_bytes"] / 1e9, LOCAL_BYTES_PER_TET * ntets / 1e9) if not args.scene else
