@@ -44,7 +44,7 @@ static void drop_iteration_graph(admmb_ctx *ctx);
 
 static void free_batch(Batch &b) {
 	b.d_idx.free(); b.d_S.free(); b.d_w.free(); b.d_wdt2.free(); b.d_kk.free(); b.d_aux.free(); b.d_u.free(); b.d_z.free();
-	b.d_state.free(); b.d_active.free(); b.d_its.free(); b.d_shape_kind.free(); b.d_shape_params.free();
+	b.d_state.free(); b.d_active.free(); b.d_its.free(); b.d_trips.free(); b.d_shape_kind.free(); b.d_shape_params.free();
 }
 
 extern "C" int admmb_destroy(admmb_ctx *ctx) {
@@ -319,6 +319,8 @@ static int upload_batch(admmb_ctx *ctx, Batch &b) {
 		ADMMB_CUDA(ctx, b.d_state.upload(st, s));
 		ADMMB_CUDA(ctx, b.d_its.alloc(b.nlocal));
 		ADMMB_CUDA(ctx, b.d_its.zero(s));
+		ADMMB_CUDA(ctx, b.d_trips.alloc(b.nlocal));
+		ADMMB_CUDA(ctx, b.d_trips.zero(s));
 	}
 	if (b.type == BT_COLLISION) {
 		ADMMB_CUDA(ctx, b.d_shape_kind.upload(b.shape_kind, s));
@@ -987,7 +989,8 @@ extern "C" long admmb_state_size(admmb_ctx *ctx, int which) {
 	case ADMMB_STATE_Z:
 	case ADMMB_STATE_U: for (const Batch &b : ctx->batches) c += (long)b.rows * b.count; return c;
 	case ADMMB_STATE_PROX: for (const Batch &b : ctx->batches) if (is_hyper(b)) c += 4L * b.count; return c;
-	case ADMMB_STATE_PROX_ITERS: for (const Batch &b : ctx->batches) if (is_hyper(b)) c += b.count; return c;
+	case ADMMB_STATE_PROX_ITERS:
+	case ADMMB_STATE_PROX_TRIALS: for (const Batch &b : ctx->batches) if (is_hyper(b)) c += b.count; return c;
 	}
 	return ADMMB_E_ARG;
 }
@@ -1042,13 +1045,14 @@ extern "C" int admmb_get_state(admmb_ctx *ctx, int which, double *out) {
 		}
 		return ADMMB_OK;
 	}
-	case ADMMB_STATE_PROX_ITERS: {
+	case ADMMB_STATE_PROX_ITERS:
+	case ADMMB_STATE_PROX_TRIALS: {
 		long o = 0;
 		for (const Batch &b : ctx->batches) {
 			if (!is_hyper(b) || b.count == 0) continue;
 			std::vector<int> its(b.nlocal);
 			if (b.nlocal < b.count) std::fill(out + o, out + o + b.count, std::nan("")); // partitioned mesh: see soa_download
-			ADMMB_CUDA(ctx, cudaMemcpyAsync(its.data(), b.d_its.p, its.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+			ADMMB_CUDA(ctx, cudaMemcpyAsync(its.data(), which == ADMMB_STATE_PROX_ITERS ? b.d_its.p : b.d_trips.p, its.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 			ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			for (int p = 0; p < b.nlocal; ++p) out[o + b.perm[p]] = (double)its[p];
 			o += b.count;

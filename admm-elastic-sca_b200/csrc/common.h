@@ -77,7 +77,7 @@ struct Batch {
 	// device, INTERNAL element order, structure-of-arrays [component][count]
 	DevBuf<int> d_idx;      // [nv][count] internal node ids
 	DevBuf<double> d_S, d_w, d_wdt2, d_kk, d_aux, d_u, d_z, d_state;
-	DevBuf<int> d_active, d_its;
+	DevBuf<int> d_active, d_its, d_trips;
 	DevBuf<int> d_shape_kind;
 	DevBuf<double> d_shape_params;
 };

@@ -130,7 +130,7 @@ static void fill_local_args(admmb_ctx *ctx, Batch &b, const double *d_x, LocalAr
 	memset(&a, 0, sizeof(a));
 	a.count = b.nlocal;
 	a.idx = b.d_idx.p; a.S = b.d_S.p; a.w = b.d_w.p; a.wdt2 = b.d_wdt2.p; a.kk = b.d_kk.p; a.aux = b.d_aux.p;
-	a.u = b.d_u.p; a.z = b.d_z.p; a.state = b.d_state.p; a.its = b.d_its.p; a.active = b.d_active.p;
+	a.u = b.d_u.p; a.z = b.d_z.p; a.state = b.d_state.p; a.its = b.d_its.p; a.trips = b.d_trips.p; a.active = b.d_active.p;
 	a.x = d_x;
 	a.P = ctx->d_P.p + 3 * (size_t)b.slot_base;
 	a.p0 = b.p0; a.p1 = b.p1; a.p2 = b.p2; a.max_iterations = b.max_iterations; a.flag = b.flag;

@@ -18,6 +18,7 @@ struct LocalArgs {
 	double *u, *z;        // [rows][count]
 	double *state;        // [nstate][count]
 	int *its;             // [count] or null
+	int *trips;           // [count] or null: line-search trial points of the last project() (diagnostics: lane divergence)
 	const int *active;    // moving anchors
 	const double *x;      // [n][3]
 	double *P;            // [slots][3], already offset to this batch's first slot
@@ -111,7 +112,9 @@ ADMMB_HD void local_tet_hyper(const LocalArgs &a, const int e, double *park, con
 	// initial guess needs positive entries; collapsed-node test case (TetForce.cpp:339-347)
 	if (x2[2] < 0.0) { x2[2] *= -1.0; }
 	else if (fabs(x2[0]) < 1.e-3 && fabs(x2[1]) < 1.e-3 && fabs(x2[2]) < 1.e-3) { x2[0] = 1.e-3; x2[1] = 1.e-3; x2[2] = 1.e-3; }
-	const int its = lbfgs_minimize<Model, ProxParams, 3, MH>(P, x2, a.max_iterations, 1e-8, ih);
+	int trips = 0;
+	const int its = lbfgs_minimize<Model, ProxParams, 3, MH>(P, x2, a.max_iterations, 1e-8, ih, &trips);
+	if (a.trips) a.trips[e] = trips;
 	a.state[e] = x2[0]; a.state[(size_t)n + e] = x2[1]; a.state[2 * (size_t)n + e] = x2[2]; a.state[3 * (size_t)n + e] = ih;
 	if (a.its) a.its[e] = its;
 

@@ -56,7 +56,9 @@ enum {
 	ADMMB_STATE_U = 2,     /* curr_u (System.hpp:96), same layout                                      */
 	ADMMB_STATE_PROX = 3,  /* per HyperElasticTet: last_prox_result[3] + solver init_hess (TetForce.hpp:145,
 	                          cppoptlib/meta.h:33), 4 doubles each, force order                        */
-	ADMMB_STATE_PROX_ITERS = 4 /* per HyperElasticTet: L-BFGS n_iters of the last project(), as doubles */
+	ADMMB_STATE_PROX_ITERS = 4, /* per HyperElasticTet: L-BFGS n_iters of the last project(), as doubles */
+	ADMMB_STATE_PROX_TRIALS = 5 /* per HyperElasticTet: line-search trial points of the last project() (MoreThuente nfev summed
+	                               over its L-BFGS iterations), as doubles: diagnostics of the local step's lane divergence */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
