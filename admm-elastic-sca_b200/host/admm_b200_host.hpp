@@ -55,6 +55,7 @@ public:
 	virtual B200Class b200_class() const = 0;
 	virtual bool b200_same_batch(const Force &) const { return true; } // same class assumed by the caller
 	virtual int b200_rows() const = 0;
+	virtual bool b200_is_batch() const { return false; } // ForceBatch below: ONE object for a whole run of elements
 };
 
 class Spring : public Force {
@@ -172,6 +173,75 @@ public:
 	bool b200_same_batch(const Force &o) const {
 		const BendForce *t = dynamic_cast<const BendForce *>(&o);
 		return t && t->stiffness == stiffness;
+	}
+};
+
+// ---- SoA batches (not in the reference API) ----------------------------------------------------
+// ONE Force object that describes a whole run of equal elements: the corner indices as one flat array, the material once.
+// System::initialize() hands the arrays to admmb_add_* as they are -- no heap object, no virtual call and no copy per
+// element, which is what the reference's ForceBuilder costs (ForceBuilder.cpp:310-313,346-349: one shared_ptr<Force> per
+// tet) and what makes an 8 M-tet scene slow to load.  A batch sits in System::forces like any other force (so the order
+// of the rows of z / u is the order of the list, as in the reference); `weights` holds the per-element ADMM weights after
+// initialize() and may be edited before recompute_weights(), like Force::weight.  host/scene/ForceBuilderBatched.cpp builds
+// these from the reference's XML vocabulary.
+class ForceBatch : public Force {
+public:
+	std::vector<int> idx;        // corners, element-major
+	std::vector<double> weights; // one per element (Force::weight of the batch object itself is unused)
+	size_t count() const { return idx.size() / (size_t)b200_corners(); }
+	bool b200_is_batch() const { return true; }
+	int b200_rows() const { return (int)count() * b200_rows_per_element(); }
+	virtual int b200_corners() const = 0;
+	virtual int b200_rows_per_element() const = 0;
+	virtual int b200_add(admmb_ctx *ctx) const = 0; // registers the batch, returns the device batch id (< 0: error)
+};
+
+class TetBatch : public ForceBatch { // TetForce.hpp:31-147
+public:
+	// kind: ADMMB_TET_LINEAR_STRAIN (p0 = stiffness), ADMMB_TET_VOLUME (stiffness, range_min, range_max),
+	// ADMMB_TET_NEOHOOKEAN / ADMMB_TET_STVK (mu, lambda; max_iterations)
+	TetBatch(int kind_, double p0_, double p1_ = 0.0, double p2_ = 0.0, int max_iterations_ = 0)
+	    : kind(kind_), max_iterations(max_iterations_) { p[0] = p0_; p[1] = p1_; p[2] = p2_; }
+	int kind, max_iterations;
+	double p[3];
+	B200Class b200_class() const { return B_TET; }
+	int b200_corners() const { return 4; }
+	int b200_rows_per_element() const { return 9; }
+	int b200_add(admmb_ctx *ctx) const { return admmb_add_tets(ctx, kind, (int)count(), idx.data(), p[0], p[1], p[2], max_iterations); }
+};
+
+class TriangleBatch : public ForceBatch { // LimitedTriangleStrain, TriangleForce.hpp:31-62
+public:
+	TriangleBatch(double stiffness_, double limit_min_, double limit_max_, bool strain_limiting_ = true)
+	    : stiffness(stiffness_), limit_min(limit_min_), limit_max(limit_max_), strain_limiting(strain_limiting_) {}
+	double stiffness, limit_min, limit_max;
+	bool strain_limiting;
+	B200Class b200_class() const { return B_TRI; }
+	int b200_corners() const { return 3; }
+	int b200_rows_per_element() const { return 6; }
+	int b200_add(admmb_ctx *ctx) const { return admmb_add_tris(ctx, ADMMB_TRI_LIMITED_STRAIN, (int)count(), idx.data(), stiffness, limit_min, limit_max, strain_limiting ? 1 : 0); }
+};
+
+class BendBatch : public ForceBatch { // BendForce.hpp:31-60; idx = the four hinge vertices in the reference's (Volino) order
+public:
+	explicit BendBatch(double stiffness_) : stiffness(stiffness_) {}
+	double stiffness;
+	B200Class b200_class() const { return B_BEND; }
+	int b200_corners() const { return 4; }
+	int b200_rows_per_element() const { return 9; }
+	int b200_add(admmb_ctx *ctx) const { return admmb_add_bends(ctx, (int)count(), idx.data(), stiffness); }
+};
+
+class SpringBatch : public ForceBatch { // Force.hpp:78-95
+public:
+	explicit SpringBatch(double stiffness_) : stiffness(stiffness_) {}
+	double stiffness;
+	B200Class b200_class() const { return B_SPRING; }
+	int b200_corners() const { return 2; }
+	int b200_rows_per_element() const { return 3; }
+	int b200_add(admmb_ctx *ctx) const {
+		const std::vector<double> k(count(), stiffness);
+		return admmb_add_springs(ctx, (int)count(), idx.data(), k.data());
 	}
 };
 
@@ -401,7 +471,7 @@ protected:
 			pinned_bytes[k] = ok ? bytes[k] : 0;
 		}
 	}
-	struct BatchRef { int id; Force::B200Class cls; size_t first, count; std::vector<double> pos; std::vector<int> act; bool any_inactive; };
+	struct BatchRef { int id; Force::B200Class cls; size_t first, count; std::vector<double> pos; std::vector<int> act; bool any_inactive; bool soa; };
 	std::vector<BatchRef> batches;
 	// explicit forces as registered on the device at initialize(): the object, its device id and the direction last sent
 	struct ExplicitRef { const ExplicitForce *obj; int id; double dir[3]; };
@@ -450,8 +520,23 @@ inline bool System::initialize() {
 	long row = 0;
 	while (i < forces.size()) {
 		Force *f0 = forces[i].get();
+		if (f0->b200_is_batch()) { // an SoA batch goes to the device as it is
+			ForceBatch *fb = static_cast<ForceBatch *>(f0);
+			fb->global_idx = (int)row;
+			if (fb->count() > 0) {
+				if (fb->idx.size() != fb->count() * (size_t)fb->b200_corners()) { std::cerr << "\n**Solver Error: ragged force batch" << std::endl; return false; }
+				const int bid = fb->b200_add(ctx);
+				if (bid < 0) return fail("add forces");
+				BatchRef br;
+				br.id = bid; br.cls = fb->b200_class(); br.first = i; br.count = fb->count(); br.any_inactive = false; br.soa = true;
+				batches.push_back(br);
+				row += fb->b200_rows();
+			}
+			++i;
+			continue;
+		}
 		size_t j = i + 1;
-		while (j < forces.size() && forces[j]->b200_class() == f0->b200_class() && f0->b200_same_batch(*forces[j])) ++j;
+		while (j < forces.size() && !forces[j]->b200_is_batch() && forces[j]->b200_class() == f0->b200_class() && f0->b200_same_batch(*forces[j])) ++j;
 		const int cnt = (int)(j - i);
 		int id = -1;
 		std::vector<int> idx;
@@ -522,7 +607,7 @@ inline bool System::initialize() {
 			admmb_set_batch_weights(ctx, id, w.data());
 		}
 		BatchRef br;
-		br.id = id; br.cls = f0->b200_class(); br.first = i; br.count = (size_t)cnt; br.any_inactive = false;
+		br.id = id; br.cls = f0->b200_class(); br.first = i; br.count = (size_t)cnt; br.any_inactive = false; br.soa = false;
 		if (br.cls == Force::B_MOVING_ANCHOR) { // what the device holds: the positions just sent, all active
 			br.pos.resize(3 * (size_t)cnt);
 			br.act.assign(cnt, 1);
@@ -554,6 +639,12 @@ inline bool System::initialize() {
 	if (admmb_finalize(ctx, settings.timestep_s) < 0) return fail("finalize");
 	// read back the weights the library computed (Force::initialize in the reference)
 	for (size_t b = 0; b < batches.size(); ++b) {
+		if (batches[b].soa) {
+			ForceBatch *fb = static_cast<ForceBatch *>(forces[batches[b].first].get());
+			fb->weights.resize(batches[b].count);
+			if (admmb_get_batch_weights(ctx, batches[b].id, fb->weights.data()) < 0) return fail("get weights");
+			continue;
+		}
 		std::vector<double> w(batches[b].cls == Force::B_COLLISION ? (size_t)n : batches[b].count);
 		if (admmb_get_batch_weights(ctx, batches[b].id, w.data()) < 0) return fail("get weights");
 		if (batches[b].cls == Force::B_COLLISION) forces[batches[b].first]->weight = w.empty() ? 0.0 : w[0];
@@ -626,6 +717,11 @@ inline void System::recompute_weights() {
 	if (!ctx) return;
 	const int n = (int)(m_x.size() / 3);
 	for (size_t b = 0; b < batches.size(); ++b) {
+		if (batches[b].soa) {
+			const ForceBatch *fb = static_cast<const ForceBatch *>(forces[batches[b].first].get());
+			if (fb->weights.size() == batches[b].count) admmb_set_batch_weights(ctx, batches[b].id, fb->weights.data());
+			continue;
+		}
 		std::vector<double> w(batches[b].cls == Force::B_COLLISION ? (size_t)n : batches[b].count);
 		if (batches[b].cls == Force::B_COLLISION) std::fill(w.begin(), w.end(), forces[batches[b].first]->weight);
 		else for (size_t k = 0; k < batches[b].count; ++k) w[k] = forces[batches[b].first + k]->weight;

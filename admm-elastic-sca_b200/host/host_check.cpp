@@ -27,8 +27,12 @@ public:
 };
 
 int main(int argc, char **argv) {
-	if (argc < 3) { fprintf(stderr, "usage: host_check scene.txt out.bin [userforce]\n"); return 2; }
+	if (argc < 3) { fprintf(stderr, "usage: host_check scene.txt out.bin [userforce|soa]\n"); return 2; }
 	const bool userforce = argc > 3 && std::string(argv[3]) == "userforce";
+	// "soa": runs of tets / strain triangles / bends / uniform springs go into ONE ForceBatch object each (what
+	// host/scene/ForceBuilderBatched.cpp builds) instead of one Force object per element; everything else as before
+	const bool soa = argc > 3 && std::string(argv[3]) == "soa";
+	std::vector<std::shared_ptr<ForceBatch> > soa_batches;
 	std::ifstream in(argv[1]);
 	if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
 	Solver system; // the later releases' name of admm::System (alias)
@@ -49,6 +53,31 @@ int main(int argc, char **argv) {
 		int kind, count, maxit, flag;
 		double p0, p1, p2;
 		in >> type >> kind >> count >> p0 >> p1 >> p2 >> maxit >> flag;
+		if (soa && (type == "tets" || (type == "tris" && kind == 0) || type == "bends" || type == "springs")) {
+			std::shared_ptr<ForceBatch> fb;
+			const int corners = type == "tris" ? 3 : (type == "springs" ? 2 : 4);
+			std::vector<int> idx((size_t)corners * count);
+			std::vector<double> ks(count, 0.0);
+			for (int e = 0; e < count; ++e) {
+				for (int c = 0; c < corners; ++c) in >> idx[(size_t)corners * e + c];
+				if (type == "springs") in >> ks[e];
+			}
+			bool uniform = true;
+			for (int e = 1; e < count; ++e) uniform = uniform && ks[e] == ks[0];
+			static const int tet_kinds[4] = { ADMMB_TET_LINEAR_STRAIN, ADMMB_TET_NEOHOOKEAN, ADMMB_TET_STVK, ADMMB_TET_VOLUME };
+			if (type == "tets") fb.reset(new TetBatch(tet_kinds[kind], p0, p1, p2, (kind == 1 || kind == 2) ? maxit : 0));
+			else if (type == "tris") fb.reset(new TriangleBatch(p0, p1, p2, flag != 0));
+			else if (type == "bends") fb.reset(new BendBatch(p0));
+			else if (uniform && count > 0) fb.reset(new SpringBatch(ks[0]));
+			if (fb) {
+				fb->idx = idx;
+				soa_batches.push_back(fb);
+				system.add_force(fb);
+			} else {
+				for (int e = 0; e < count; ++e) system.add_force(std::shared_ptr<Force>(new Spring(idx[2 * e], idx[2 * e + 1], ks[e])));
+			}
+			continue;
+		}
 		for (int e = 0; e < count; ++e) {
 			std::shared_ptr<Force> f;
 			int i0, i1, i2, i3;
@@ -123,12 +152,18 @@ int main(int argc, char **argv) {
 	if (!in) { fprintf(stderr, "scene file truncated\n"); return 2; }
 	if (!system.initialize()) return 1;
 	if (has_after) system.m_x = x_after;
+	for (size_t b = 0; b < soa_batches.size(); ++b) { // the weights initialize() computed are visible per element, like Force::weight
+		if (soa_batches[b]->weights.size() != soa_batches[b]->count()) { fprintf(stderr, "batch %zu: weights not read back\n", b); return 1; }
+		for (size_t e = 0; e < soa_batches[b]->count(); ++e)
+			if (!(soa_batches[b]->weights[e] > 0.0)) { fprintf(stderr, "batch %zu: weight %zu = %g\n", b, e, soa_batches[b]->weights[e]); return 1; }
+	}
+	if (soa) system.recompute_weights(); // pushes the (unchanged) per-element weights back and refactors: same numbers
 	FILE *out = fopen(argv[2], "wb");
 	for (int f = 0; f < frames; ++f) {
 		if (!system.step()) return 1;
 		fwrite(system.m_x.data(), sizeof(double), 3 * n, out);
 	}
 	fclose(out);
-	printf("host_check: %d nodes, %zu forces, %d frames, elapsed %.3f s\n", n, system.forces.size(), frames, system.elapsed_s);
+	printf("host_check: %d nodes, %zu force objects (%zu SoA batches), %d frames, elapsed %.3f s\n", n, system.forces.size(), soa_batches.size(), frames, system.elapsed_s);
 	return 0;
 }

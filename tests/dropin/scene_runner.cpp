@@ -6,8 +6,10 @@
 // mains do around SimContext (the mains need GLFW): samples/*/ *.cpp setup(), cited below.
 //
 //   ref_scene_runner <bunnyexpand|windyflag|poordillo|plinkopony> <scene.xml> <frames> <out.bin>
+//   ref_scene_runner dump-forces <scene.xml> <out.txt>
 //
 // out.bin: frames x 3n doubles, m_x after every SimContext::step.
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <random>
@@ -24,7 +26,59 @@ static double smooth(double t, double t0, double t1) { // helper::smooth_move, A
 	return 3.0 * r * r - 2.0 * r * r * r;
 }
 
+// `dump-forces`: the force list the scene layer built while loading the XML (ForceBuilder::admm_build_object ->
+// build_tetmesh / build_trimesh), one line per ELEMENT whether it sits in the list as its own object (src/ForceBuilder.cpp) or
+// inside an SoA batch (host/scene/ForceBuilderBatched.cpp); needs no GPU.  The two runners must print the same text.
+static int dump_forces(const char *xml, const char *path) {
+	SimContext context;
+	context.system->settings.verbose = 0;
+	const auto t0 = std::chrono::steady_clock::now();
+	context.load(xml);
+	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	FILE *o = fopen(path, "w");
+	if (!o) return 2;
+	size_t objects = 0, elements = 0;
+	const std::vector<std::shared_ptr<Force> > &F = context.system->forces;
+	for (size_t k = 0; k < F.size(); ++k, ++objects) {
+		const Force *f = F[k].get();
+		if (const TetBatch *b = dynamic_cast<const TetBatch *>(f)) {
+			for (size_t e = 0; e < b->count(); ++e, ++elements)
+				fprintf(o, "tet %d %.17g %.17g %.17g %d : %d %d %d %d\n", b->kind, b->p[0], b->p[1], b->p[2], b->max_iterations, b->idx[4 * e], b->idx[4 * e + 1], b->idx[4 * e + 2], b->idx[4 * e + 3]);
+		} else if (const TetBase *t = dynamic_cast<const TetBase *>(f)) {
+			double p0, p1, p2; int m;
+			t->b200_params(p0, p1, p2, m);
+			fprintf(o, "tet %d %.17g %.17g %.17g %d : %d %d %d %d\n", t->b200_kind(), p0, p1, p2, m, t->idx[0], t->idx[1], t->idx[2], t->idx[3]);
+			++elements;
+		} else if (const TriangleBatch *b = dynamic_cast<const TriangleBatch *>(f)) {
+			for (size_t e = 0; e < b->count(); ++e, ++elements)
+				fprintf(o, "tri %.17g %.17g %.17g %d : %d %d %d\n", b->stiffness, b->limit_min, b->limit_max, b->strain_limiting ? 1 : 0, b->idx[3 * e], b->idx[3 * e + 1], b->idx[3 * e + 2]);
+		} else if (const LimitedTriangleStrain *t = dynamic_cast<const LimitedTriangleStrain *>(f)) {
+			fprintf(o, "tri %.17g %.17g %.17g %d : %d %d %d\n", t->stiffness, t->limit_min, t->limit_max, t->b200_flag(), t->id0, t->id1, t->id2);
+			++elements;
+		} else if (const BendBatch *b = dynamic_cast<const BendBatch *>(f)) {
+			for (size_t e = 0; e < b->count(); ++e, ++elements)
+				fprintf(o, "bend %.17g : %d %d %d %d\n", b->stiffness, b->idx[4 * e], b->idx[4 * e + 1], b->idx[4 * e + 2], b->idx[4 * e + 3]);
+		} else if (const BendForce *t = dynamic_cast<const BendForce *>(f)) {
+			fprintf(o, "bend %.17g : %d %d %d %d\n", t->stiffness, t->idx[0], t->idx[1], t->idx[2], t->idx[3]);
+			++elements;
+		} else if (const SpringBatch *b = dynamic_cast<const SpringBatch *>(f)) {
+			for (size_t e = 0; e < b->count(); ++e, ++elements) fprintf(o, "spring %.17g : %d %d\n", b->stiffness, b->idx[2 * e], b->idx[2 * e + 1]);
+		} else if (const Spring *t = dynamic_cast<const Spring *>(f)) {
+			fprintf(o, "spring %.17g : %d %d\n", t->stiffness, t->idx0, t->idx1);
+			++elements;
+		} else {
+			fprintf(o, "other\n");
+			++elements;
+		}
+	}
+	fprintf(o, "nodes %ld bend_index %d\n", (long)(context.system->m_x.size() / 3), ForceBuilder::bend_index);
+	fclose(o);
+	printf("load %.3f s, %zu force objects, %zu elements\n", sec, objects, elements);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc == 4 && std::string(argv[1]) == "dump-forces") return dump_forces(argv[2], argv[3]);
 	if (argc < 5) { fprintf(stderr, "usage: ref_scene_runner <scene> <scene.xml> <frames> <out.bin>\n"); return 2; }
 	const std::string which = argv[1];
 	const int frames = atoi(argv[3]);

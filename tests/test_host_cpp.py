@@ -153,3 +153,25 @@ def test_user_defined_explicit_force_keeps_all_explicit_forces_on_the_host(tmp_p
     err = max(rel_l2(xs[1][f], xs[0][f]) for f in range(frames))
     print(f"device explicit forces vs host explicit forces (user subclass present): rel-L2 {err:.1e}")
     assert err <= 1e-10   # the solve accumulates with atomics (last bits vary) and the wind drag amplifies that ~3x per frame
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_soa_force_batches_are_bit_identical_to_one_object_per_force(name, tmp_path):
+    """SURVEY section 8 row f4: a run of elements registered as ONE admm::TetBatch / TriangleBatch / BendBatch / SpringBatch object
+    (what host/scene/ForceBuilderBatched.cpp builds) must give the same frames, bit for bit, as the reference's one heap
+    object per element; the per-element weights are read back into the batch and survive recompute_weights()."""
+    binary = _need("host_check")
+    sc = scenes.load_scene(os.path.join(GOLDEN, f"{name}.scene.npz"))
+    frames = SCEN[name]["frames"]
+    txt = str(tmp_path / "scene.txt")
+    write_scene_txt(txt, sc, frames)
+    env = dict(os.environ, ADMMB_DETERMINISTIC="1")
+    xs, notes = [], []
+    for mode in ([], ["soa"]):
+        out = str(tmp_path / f"x{len(mode)}.bin")
+        r = subprocess.run([binary, txt, out] + mode, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        xs.append(np.fromfile(out, dtype=np.float64).reshape(frames, -1))
+        notes.append(r.stdout.strip().splitlines()[-1])
+    print(f"{name}: {notes[0]} | {notes[1]}")
+    assert np.array_equal(xs[0], xs[1])

@@ -11,6 +11,9 @@ sc = scenes.cube_scene(N, kind=scenes.TET_NH, mu=1e5, lam=1e5, maxit=5, mass=100
 sim = admm_b200.System(sc)
 sim.set_x(sc["x_after_init"]); sim.upload()
 sim.step_resident(frames=25)
+sim.step_resident(frames=20)                       # the frames bench.py times (10 iterations each)
+h = np.bincount(sim.state(5).astype(np.int32), minlength=22)
+print("bench regime, last iteration of frame 45: trial-count histogram", h, " share with 2 trials %.3f, with 20 %.3f, mean %.2f" % (h[2] / h.sum(), h[20] / h.sum(), (h * np.arange(len(h))).sum() / h.sum()))
 tr = []
 for k in range(4):
     sim.step_resident(frames=1, iters=1)          # one ADMM iteration per call: consecutive local steps
