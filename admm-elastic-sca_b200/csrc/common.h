@@ -226,6 +226,9 @@ void pcg_destroy(admmb_ctx *ctx);
 // dist.cu
 int dist_allgather_nodes(admmb_ctx *ctx, double *vec);            // in place: every rank contributes its owned rows
 int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count);
+int dist_halo_exchange(admmb_ctx *ctx, const double *send_buf, const int *send_off, const int *send_cnt, double *recv_base, const int *recv_off, const int *recv_cnt);
+int dist_allgather_host(admmb_ctx *ctx, const void *mine, void *all, size_t bytes);  // setup-time, synchronises
+int dist_allreduce_host_int(admmb_ctx *ctx, int *value);                                  // setup-time sum / barrier
 void dist_destroy(admmb_ctx *ctx);
 // front_gpu.cu
 struct FrontBackend;

@@ -4,13 +4,15 @@
 // contiguous chunk [own0, own1) of it.  Per ADMM iteration a rank
 //   * runs the local step for the forces that touch an owned node (boundary forces are evaluated on both sides,
 //     bit-identically, so the owned rows of the right-hand side are complete without any exchange),
-//   * runs Jacobi-PCG on its rows of A_n; the only data-path collectives are an all-gather of the search direction p
-//     before each SpMV (each rank contributes its owned rows; over NVSwitch this is the halo exchange in its simplest
-//     form -- 3 n doubles in total, 4.2 MB at 1 M tets) and all-reduces of 3 / 6 doubles for the dot products,
-//   * all-gathers the solution so that every rank holds curr_x for the next local step.
+//   * direct solver (default): all-gathers the right-hand side and runs the solve sharded by subtrees of the elimination
+//     tree (direct_solve.cu, shard_owners) -- one all-reduce of the top separator rows, one all-reduce of x -- or
+//     replicated (deterministic mode / ADMMB_DIST_SOLVE=replicated),
+//   * PCG: runs Jacobi-PCG on its rows of A_n; per CG iteration the data-path exchanges are a neighbour-only halo of the
+//     preconditioned residual u (grouped ncclSend / ncclRecv of exactly the nodes a peer's rows reference: the separator
+//     surfaces between the chunks, dist_halo_exchange) and ONE all-reduce of 9 doubles for the fused dot products; the
+//     solution is all-gathered once per solve so that every rank holds curr_x for the next local step.
 // x and v stay replicated (frame begin / end are evaluated redundantly), so the C ABI is unchanged: every rank makes
-// the same calls with the same data.  The direct solver does not shard (sparse triangular solves are a dependency
-// chain): admmb_finalize rejects it for world > 1 -- replicas only.
+// the same calls with the same data.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -30,6 +32,10 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 } g_nccl;
@@ -44,8 +50,13 @@ bool nccl_load() {
 	g_nccl.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
 	g_nccl.AllGather = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
 	g_nccl.AllReduce = (ncclResult_t(*)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+	g_nccl.Send = (ncclResult_t(*)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+	g_nccl.Recv = (ncclResult_t(*)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+	g_nccl.GroupStart = (ncclResult_t(*)())dlsym(h, "ncclGroupStart");
+	g_nccl.GroupEnd = (ncclResult_t(*)())dlsym(h, "ncclGroupEnd");
 	g_nccl.GetErrorString = (const char *(*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
-	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString;
+	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.Send && g_nccl.Recv &&
+	            g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
 	return g_nccl.ok;
 }
 } // namespace
@@ -95,6 +106,57 @@ int dist_allgather_nodes(admmb_ctx *ctx, double *vec) {
 int dist_allreduce_sum(admmb_ctx *ctx, double *dev, int count) {
 	if (ctx->dist_world == 1) return ADMMB_OK;
 	ADMMB_NCCL(ctx, g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return ADMMB_OK;
+}
+
+// Neighbour-only halo exchange: one grouped send / receive per peer this rank shares matrix entries with.  send_buf holds the
+// packed values for all peers (3 doubles per node), peer q's slice at node offset send_off[q]; the values from q land at
+// recv_base + 3 * recv_off[q].
+int dist_halo_exchange(admmb_ctx *ctx, const double *send_buf, const int *send_off, const int *send_cnt, double *recv_base, const int *recv_off, const int *recv_cnt) {
+	if (ctx->dist_world == 1) return ADMMB_OK;
+	ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+	ADMMB_NCCL(ctx, g_nccl.GroupStart());
+	for (int q = 0; q < ctx->dist_world; ++q) {
+		if (q == ctx->dist_rank) continue;
+		if (send_cnt[q] > 0) ADMMB_NCCL(ctx, g_nccl.Send(send_buf + 3 * (size_t)send_off[q], 3 * (size_t)send_cnt[q], ncclDouble, q, comm, ctx->stream));
+		if (recv_cnt[q] > 0) ADMMB_NCCL(ctx, g_nccl.Recv(recv_base + 3 * (size_t)recv_off[q], 3 * (size_t)recv_cnt[q], ncclDouble, q, comm, ctx->stream));
+	}
+	ADMMB_NCCL(ctx, g_nccl.GroupEnd());
+	return ADMMB_OK;
+}
+
+// every rank contributes `bytes` host bytes; `all` receives world x bytes in rank order (setup-time exchange of IPC handles)
+int dist_allgather_host(admmb_ctx *ctx, const void *mine, void *all, size_t bytes) {
+	if (ctx->dist_world == 1) { memcpy(all, mine, bytes); return ADMMB_OK; }
+	DevBuf<char> d;
+	ADMMB_CUDA(ctx, d.alloc(bytes * ctx->dist_world));
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(d.p + bytes * ctx->dist_rank, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ncclResult_t r = g_nccl.AllGather(d.p + bytes * ctx->dist_rank, d.p, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+	cudaError_t e = cudaSuccess;
+	if (r == ncclSuccess) e = cudaMemcpyAsync(all, d.p, bytes * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->stream);
+	if (r == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	d.free();
+	if (r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "ncclAllGather -> %s", g_nccl.GetErrorString(r));
+	ADMMB_CUDA(ctx, e);
+	return ADMMB_OK;
+}
+
+// sum of one host int over the ranks (setup-time agreement / barrier); synchronises the stream
+int dist_allreduce_host_int(admmb_ctx *ctx, int *value) {
+	if (ctx->dist_world == 1) return ADMMB_OK;
+	DevBuf<double> d;
+	ADMMB_CUDA(ctx, d.alloc(1));
+	const double v = (double)*value;
+	double out = 0.0;
+	ADMMB_CUDA(ctx, cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	ncclResult_t r = g_nccl.AllReduce(d.p, d.p, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+	cudaError_t e = cudaSuccess;
+	if (r == ncclSuccess) e = cudaMemcpyAsync(&out, d.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (r == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	d.free();
+	if (r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "ncclAllReduce -> %s", g_nccl.GetErrorString(r));
+	ADMMB_CUDA(ctx, e);
+	*value = (int)out;
 	return ADMMB_OK;
 }
 

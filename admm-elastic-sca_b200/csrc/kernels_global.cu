@@ -7,6 +7,8 @@
 //   frame end     v = (curr_x - x) / dt, x = curr_x                               (System.cpp:70-71)
 //
 // All node vectors are [n][3] interleaved, internal (nested-dissection) node order.
+#include <algorithm>
+
 #include "common.h"
 
 namespace admmb {
@@ -170,7 +172,41 @@ int launch_rhs(admmb_ctx *ctx) {
 // "done" flag (kernels of a finished solve return at once); the host looks at the flag once per batch of chunks, sized
 // from the previous solve's iteration count, so a solve normally costs one host synchronisation.
 // =====================================================================================================
+#define PCG_MAXW 16
+// Peer-to-peer exchange state handed to the CG kernels by value (world == 1: every loop below vanishes).
+// flag ints (S.flag): [0] done, [1] iterations, [2] stagnation count, [3] p2p time-out, [4] halo pushes made, [5] dot pushes
+// made, [6] blocks finished (last-block detection).  All ranks run the same kernel sequence, so "the n-th push" is the same
+// event everywhere: a rank waits until a peer's flag reaches its OWN push count.
+struct PeerArgs {
+	int world = 1, rank = 0;
+	const int *send_idx = nullptr;        // owned nodes the peers' rows reference, grouped by peer
+	int send_off[PCG_MAXW + 1] = {};      // peer q's slice of send_idx
+	int recv_cnt[PCG_MAXW] = {};          // nodes received from q (0: nothing to wait for)
+	double *peer_halo[PCG_MAXW] = {};     // where this rank's slice lands in q's u (q's slots for this rank)
+	double *peer_dots[PCG_MAXW] = {};     // q's mail + rank * 24: this rank's partial dots, [parity][12]
+	int *peer_flags[PCG_MAXW] = {};       // q's flag words: [rank] halo, [world + 2 rank + parity] dots
+	const double *dots_in = nullptr;      // own mail
+	int *flags_in = nullptr;              // own flag words
+};
+
 struct PcgSolver {
+	// partitioned rows: neighbour-only halo of u.  Columns owned by a peer are remapped (idxu) to slots behind the padded
+	// vector, u[3 * (npad_nodes + slot)], which the peer's values are received into directly; send_idx lists the owned nodes
+	// the peers need, grouped by peer.  ADMMB_PCG_HALO=0 falls back to an all-gather of the whole vector (round 1).
+	bool halo = false;
+	// p2p: the halo values and the partial dot products are written straight into the peers' memory over NVLink by the CG
+	// kernels themselves (CUDA IPC mappings, release / acquire flags) -- no NCCL call inside the CG loop.  Falls back to the
+	// grouped ncclSend / ncclRecv halo + ncclAllReduce when the mappings cannot be made (ADMMB_PCG_P2P=0 forces that).
+	bool p2p = false;
+	DevBuf<double> mail;                 // [world][2 parities][12] partial dots written by the peers, then the flags (ints)
+	std::vector<void *> peer_u, peer_mail; // IPC mappings of the peers' u and mail
+	std::vector<int> peer_recv_off;      // where this rank's values go in peer q's halo slots
+	PeerArgs peer;                       // what the kernels get (world = 1 unless p2p)
+	DevBuf<int> idxu, send_idx;
+	DevBuf<double> send_buf;
+	std::vector<int> send_off, send_cnt, recv_off, recv_cnt;
+	int send_total = 0, recv_total = 0;
+	size_t npad_nodes = 0;
 	DevBuf<int> ptr, idx;
 	DevBuf<double> val, dinv;
 	DevBuf<double> r, u, w, p, s;
@@ -186,12 +222,81 @@ struct PcgSolver {
 #define PCG_THREADS 256
 #define PCG_CHUNK 16
 // scal: [0..8] gamma, delta, rr of parity 0; [9..11] b.b; [12..20] the same dots of parity 1; [21..26] alpha_old, gamma_old
-// read by parity 0 (written by parity 1); [27..32] the same read by parity 1; [33] best residual seen (stagnation guard)
+// read by parity 0 (written by parity 1); [27..32] the same read by parity 1; [33] best residual seen (stagnation guard);
+// [34..36] b.b over all ranks
 #define S_DOTS(q) (12 * (q))
 #define S_BB 9
 #define S_STATE(q) (21 + 6 * (q))
 #define S_BEST 33
+#define S_BBG 34 /* b.b summed over the ranks (peer-to-peer exchange) */
 #define S_SIZE 40
+
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+	int v;
+	asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+// bounded spin (about a second): a peer that never arrives sets flag[3] and lets the kernels drain instead of hanging the GPU
+__device__ __noinline__ void peer_wait(const int *word, int want, int *flag) {
+	if (flag[3]) return;
+	for (int spin = 0; spin < (1 << 24); ++spin) {
+		if (ld_acquire_sys(word) >= want) return;
+		__nanosleep(64);
+	}
+	flag[3] = 1;
+}
+// true in exactly one block: the last one to get here (call from all threads after the block's global writes)
+__device__ __forceinline__ bool last_block_done(int *counter) {
+	__shared__ int last;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int t = atomicAdd(counter, 1);
+		last = (t == (int)gridDim.x - 1);
+		if (last) *counter = 0;
+	}
+	__syncthreads();
+	if (last) __threadfence();
+	return last != 0;
+}
+// last block of the kernel that produced u: write the nodes the peers need into their halo slots, then raise their flags
+__device__ __forceinline__ void push_halo(const PeerArgs &P, const double *u, int *flag) {
+	for (int q = 0; q < P.world; ++q) {
+		const int c0 = 3 * P.send_off[q], c1 = 3 * P.send_off[q + 1];
+		for (int t = c0 + (int)threadIdx.x; t < c1; t += blockDim.x) P.peer_halo[q][t - c0] = __ldcg(u + 3 * (size_t)P.send_idx[t / 3] + t % 3);
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int v = flag[4] + 1;
+		flag[4] = v;
+		for (int q = 0; q < P.world; ++q)
+			if (P.send_off[q + 1] > P.send_off[q]) st_release_sys(P.peer_flags[q] + P.rank, v);
+	}
+}
+// every block, before it reads halo columns of u
+__device__ __forceinline__ void wait_halo(const PeerArgs &P, int *flag) {
+	if (P.world == 1) return;
+	if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank && P.recv_cnt[threadIdx.x] > 0) peer_wait(P.flags_in + threadIdx.x, flag[4], flag);
+	__syncthreads();
+}
+// last block of the SpMV: this rank's 12 partial sums of parity q (dots, and b.b behind parity 0) to every peer
+__device__ __forceinline__ void push_dots(const PeerArgs &P, const double *scal, int q, int *flag) {
+	if (threadIdx.x < 12) {
+		const double v = __ldcg(scal + 12 * q + threadIdx.x);
+		for (int o = 0; o < P.world; ++o)
+			if (o != P.rank) P.peer_dots[o][12 * q + threadIdx.x] = v;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int v = flag[5] + 1;
+		flag[5] = v;
+		for (int o = 0; o < P.world; ++o)
+			if (o != P.rank) st_release_sys(P.peer_flags[o] + P.world + 2 * P.rank + q, v);
+	}
+}
 
 __device__ __forceinline__ void block_reduce3_atomic(double a0, double a1, double a2, double *dst) {
 	__shared__ double sh[3][PCG_THREADS / 32];
@@ -223,7 +328,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const i
                                                           const double *__restrict__ val, const double *__restrict__ dinv,
                                                           const double *__restrict__ b, const double *__restrict__ x,
                                                           double *__restrict__ r, double *__restrict__ u, double *__restrict__ p,
-                                                          double *__restrict__ s, double *scal, int *flag) {
+                                                          double *__restrict__ s, double *scal, int *flag, const PeerArgs P) {
 	double bb[3] = { 0, 0, 0 };
 	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
@@ -249,13 +354,15 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const i
 		for (int j = 0; j < 3; ++j) { scal[S_STATE(0) + j] = 1.0; scal[S_STATE(0) + 3 + j] = __longlong_as_double(0x7ff0000000000000LL); } // alpha_old = 1, gamma_old = inf: beta = 0, alpha = gamma / delta
 		flag[0] = 0; flag[1] = 0; flag[2] = 0;
 	}
+	if (P.world > 1 && last_block_done(flag + 6)) push_halo(P, u, flag);
 }
 
 // w = A u; dots[q] += (r.u, w.u, r.r)
 __global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int q, const int *__restrict__ ptr, const int *__restrict__ idx,
                                                           const double *__restrict__ val, const double *__restrict__ u,
-                                                          const double *__restrict__ r, double *__restrict__ w, double *scal, const int *flag) {
+                                                          const double *__restrict__ r, double *__restrict__ w, double *scal, int *flag, const PeerArgs P) {
 	if (flag[0]) return;
+	wait_halo(P, flag);
 	double g[3] = { 0, 0, 0 }, d[3] = { 0, 0, 0 }, rr[3] = { 0, 0, 0 };
 	for (int i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		double a[3] = { 0, 0, 0 };
@@ -274,21 +381,43 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int q, 
 	block_reduce3_atomic(g[0], g[1], g[2], scal + S_DOTS(q) + 0);
 	block_reduce3_atomic(d[0], d[1], d[2], scal + S_DOTS(q) + 3);
 	block_reduce3_atomic(rr[0], rr[1], rr[2], scal + S_DOTS(q) + 6);
+	if (P.world > 1 && last_block_done(flag + 6)) push_dots(P, scal, q, flag);
 }
 
 // convergence test on dots[q]; beta, alpha; p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = Dinv r
 __global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int q, const double *__restrict__ dinv, double *__restrict__ u,
                                                             const double *__restrict__ w, double *__restrict__ p, double *__restrict__ s,
-                                                            double *__restrict__ x, double *__restrict__ r, double *scal, int *flag, double tol2) {
+                                                            double *__restrict__ x, double *__restrict__ r, double *scal, int *flag, double tol2,
+                                                            const PeerArgs P) {
 	if (flag[0]) return;
 	const int nq = q ^ 1;
+	// the 9 dots of parity q and b.b: own partial sums, plus -- on a partitioned mesh with peer-to-peer exchange -- the peers'
+	// from the mailbox, added in rank order so that every rank gets the same bits (and takes the same decisions)
+	__shared__ double tot[12];
+	if (threadIdx.x < 12) {
+		const int t = threadIdx.x;
+		const bool bbslot = t >= 9;
+		double acc;
+		if (P.world == 1) acc = scal[bbslot ? S_BB + t - 9 : S_DOTS(q) + t];
+		else if (bbslot && q == 1) acc = scal[S_BBG + t - 9]; // b.b is exchanged behind parity 0 only; kept by the parity-0 update
+		else {
+			acc = 0.0;
+			for (int o = 0; o < P.world; ++o) {
+				if (o == P.rank) { acc += scal[12 * q + t]; continue; }
+				peer_wait(P.flags_in + P.world + 2 * o + q, flag[5], flag);
+				acc += __ldcg(P.dots_in + 24 * o + 12 * q + t);
+			}
+		}
+		tot[t] = acc;
+	}
+	__syncthreads();
 	double alpha[3], beta[3], gamma[3], rrs = 0.0;
 	bool done = true;
 	for (int j = 0; j < 3; ++j) {
-		gamma[j] = scal[S_DOTS(q) + j];
-		const double delta = scal[S_DOTS(q) + 3 + j], rr = scal[S_DOTS(q) + 6 + j];
+		gamma[j] = tot[j];
+		const double delta = tot[3 + j], rr = tot[6 + j];
 		const double a_old = scal[S_STATE(q) + j], g_old = scal[S_STATE(q) + 3 + j];
-		done = done && (rr <= tol2 * scal[S_BB + j]);
+		done = done && (rr <= tol2 * tot[9 + j]);
 		rrs += rr;
 		beta[j] = (g_old > 0.0) ? gamma[j] / g_old : 0.0;
 		const double den = delta - beta[j] * gamma[j] / a_old;
@@ -314,6 +443,7 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int q
 	if (blockIdx.x == 0 && threadIdx.x < 9) scal[S_DOTS(nq) + threadIdx.x] = 0.0; // the SpMV of this iteration accumulates here
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		for (int j = 0; j < 3; ++j) { scal[S_STATE(nq) + j] = alpha[j]; scal[S_STATE(nq) + 3 + j] = gamma[j]; }
+		if (P.world > 1 && q == 0) for (int j = 0; j < 3; ++j) scal[S_BBG + j] = tot[9 + j];
 		const int k = flag[1];
 		flag[1] = k + 1;
 		// stagnation guard: once the residual sits at rounding level CG must not be iterated further (the recurrences break
@@ -323,12 +453,126 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_update(int r0, int n, int q
 		if (k == 0 || rrs < 0.99 * scal[S_BEST]) { scal[S_BEST] = rrs; flag[2] = 0; }
 		else if (++flag[2] >= 300 || !(rrs == rrs)) flag[0] = 1;
 	}
+	if (P.world > 1 && last_block_done(flag + 6)) push_halo(P, u, flag);
+}
+
+// send_buf[t] = u[send_idx[t]] (3 doubles per node)
+__global__ void __launch_bounds__(PCG_THREADS) k_halo_pack(int count, const int *__restrict__ send_idx, const double *__restrict__ u, double *__restrict__ out, const int *flag) {
+	if (flag[0]) return;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= 3 * count) return;
+	out[t] = u[3 * (size_t)send_idx[t / 3] + t % 3];
+}
+
+static void pcg_p2p_teardown(admmb_ctx *ctx, PcgSolver &S) {
+	bool any = false;
+	for (void *q : S.peer_u) if (q) { cudaIpcCloseMemHandle(q); any = true; }
+	for (void *q : S.peer_mail) if (q) { cudaIpcCloseMemHandle(q); any = true; }
+	S.peer_u.clear(); S.peer_mail.clear();
+	// nobody frees memory a peer still has mapped: all ranks tear down together (setup and destroy are collective calls)
+	if ((any || S.p2p) && ctx->nccl_comm) { int one = 1; dist_allreduce_host_int(ctx, &one); }
+	S.p2p = false;
+	S.peer = PeerArgs();
+}
+
+// Maps every peer's u and mailbox (CUDA IPC), checks the mappings with a round of test writes and fills S.peer.  Any failure,
+// on any rank, leaves p2p off on ALL ranks (the NCCL halo path is used instead); only a failing collective is an error.
+static int pcg_p2p_setup(admmb_ctx *ctx, PcgSolver &S) {
+	const int W = ctx->dist_world, me = ctx->dist_rank;
+	S.p2p = false;
+	S.peer = PeerArgs();
+	if (W == 1 || !S.halo || W > PCG_MAXW) return ADMMB_OK;
+	if (const char *e = getenv("ADMMB_PCG_P2P")) if (e[0] == '0') return ADMMB_OK;
+	struct Table { cudaIpcMemHandle_t hu, hm; int recv_off[PCG_MAXW]; int ok; };
+	Table mine;
+	memset(&mine, 0, sizeof(mine));
+	const size_t mail_doubles = (size_t)W * 24 + (3 * (size_t)W + 1) / 2 + 1;
+	int ok = 1, rc;
+	if (S.mail.alloc(mail_doubles) != cudaSuccess || cudaMemset(S.mail.p, 0, mail_doubles * sizeof(double)) != cudaSuccess) ok = 0;
+	if (ok && cudaIpcGetMemHandle(&mine.hu, S.u.p) != cudaSuccess) ok = 0;
+	if (ok && cudaIpcGetMemHandle(&mine.hm, S.mail.p) != cudaSuccess) ok = 0;
+	for (int q = 0; q < W; ++q) mine.recv_off[q] = S.recv_off[q];
+	mine.ok = ok;
+	cudaGetLastError();
+	std::vector<Table> all(W);
+	if ((rc = dist_allgather_host(ctx, &mine, all.data(), sizeof(Table)))) return rc;
+	for (int q = 0; q < W; ++q) ok = ok && all[q].ok;
+	S.peer_u.assign(W, nullptr); S.peer_mail.assign(W, nullptr); S.peer_recv_off.assign(W, 0);
+	for (int q = 0; q < W && ok; ++q) {
+		if (q == me) continue;
+		if (cudaIpcOpenMemHandle(&S.peer_u[q], all[q].hu, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { S.peer_u[q] = nullptr; ok = 0; break; }
+		if (cudaIpcOpenMemHandle(&S.peer_mail[q], all[q].hm, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { S.peer_mail[q] = nullptr; ok = 0; break; }
+		S.peer_recv_off[q] = all[q].recv_off[me];
+	}
+	cudaGetLastError();
+	// test writes: rank r leaves 1000 + r in slot 23 of its block of every peer's mailbox (and in the last halo double it owns there)
+	if (ok) {
+		for (int q = 0; q < W; ++q) {
+			if (q == me) continue;
+			const double v = 1000.0 + me;
+			if (cudaMemcpy((double *)S.peer_mail[q] + 24 * me + 23, &v, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) ok = 0;
+			if (S.send_cnt[q] > 0 &&
+			    cudaMemcpy((double *)S.peer_u[q] + 3 * (S.npad_nodes + S.peer_recv_off[q] + S.send_cnt[q]) - 1, &v, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) ok = 0;
+		}
+		cudaDeviceSynchronize();
+		cudaGetLastError();
+	}
+	int bad = ok ? 0 : 1;
+	if ((rc = dist_allreduce_host_int(ctx, &bad))) return rc; // also the barrier between the test writes and the checks
+	if (!bad) {
+		for (int q = 0; q < W; ++q) {
+			if (q == me) continue;
+			double got[2] = { 0, 1000.0 + q };
+			cudaMemcpy(&got[0], S.mail.p + 24 * q + 23, sizeof(double), cudaMemcpyDeviceToHost);
+			if (S.recv_cnt[q] > 0) cudaMemcpy(&got[1], S.u.p + 3 * (S.npad_nodes + S.recv_off[q] + S.recv_cnt[q]) - 1, sizeof(double), cudaMemcpyDeviceToHost);
+			if (got[0] != 1000.0 + q || got[1] != 1000.0 + q) ok = 0;
+		}
+		bad = ok ? 0 : 1;
+		if ((rc = dist_allreduce_host_int(ctx, &bad))) return rc;
+	}
+	if (bad) {
+		if (getenv("ADMMB_VERBOSE")) fprintf(stderr, "[setup] rank %d: peer-to-peer mappings not available, PCG exchanges through NCCL\n", me);
+		pcg_p2p_teardown(ctx, S);
+		return ADMMB_OK;
+	}
+	cudaMemset(S.mail.p, 0, mail_doubles * sizeof(double));
+	PeerArgs &P = S.peer;
+	P.world = W; P.rank = me;
+	P.send_idx = S.send_idx.p;
+	for (int q = 0; q < W; ++q) {
+		P.send_off[q] = S.send_off[q];
+		P.recv_cnt[q] = S.recv_cnt[q];
+		if (q == me) continue;
+		P.peer_halo[q] = (double *)S.peer_u[q] + 3 * (S.npad_nodes + S.peer_recv_off[q]);
+		P.peer_dots[q] = (double *)S.peer_mail[q] + 24 * me;
+		P.peer_flags[q] = (int *)((double *)S.peer_mail[q] + 24 * W);
+	}
+	P.send_off[W] = S.send_total;
+	P.dots_in = S.mail.p;
+	P.flags_in = (int *)(S.mail.p + 24 * W);
+	S.p2p = true;
+	int one = 1;
+	if ((rc = dist_allreduce_host_int(ctx, &one))) return rc; // every mailbox is cleared before anyone starts pushing
+	if (getenv("ADMMB_VERBOSE")) fprintf(stderr, "[setup] rank %d: PCG exchanges peer to peer (CUDA IPC over NVLink), no NCCL call inside the CG loop\n", me);
+	return ADMMB_OK;
+}
+
+// u of the nodes the peers' rows reference: pack, grouped send / receive into the slots behind the vector
+static int pcg_exchange_u(admmb_ctx *ctx, PcgSolver &S) {
+	if (ctx->dist_world == 1 || S.p2p) return ADMMB_OK; // p2p: the kernel that produced u has pushed it
+	if (!S.halo) return dist_allgather_nodes(ctx, S.u.p);
+	if (S.send_total > 0) {
+		k_halo_pack<<<(3 * S.send_total + PCG_THREADS - 1) / PCG_THREADS, PCG_THREADS, 0, ctx->stream>>>(S.send_total, S.send_idx.p, S.u.p, S.send_buf.p, S.flag.p);
+		ctx->launches += 1;
+	}
+	return dist_halo_exchange(ctx, S.send_buf.p, S.send_off.data(), S.send_cnt.data(), S.u.p + 3 * S.npad_nodes, S.recv_off.data(), S.recv_cnt.data());
 }
 
 int pcg_setup(admmb_ctx *ctx) {
 	if (!ctx->pcg) ctx->pcg = new PcgSolver();
 	PcgSolver &S = *ctx->pcg;
 	const int n = ctx->n, r0 = ctx->own0, r1 = ctx->own1;
+	pcg_p2p_teardown(ctx, S); // a repeated setup (new weights) reallocates what the peers have mapped
 	// this rank's rows of A_n (all rows when the mesh is not partitioned); column indices stay global
 	std::vector<int> ptr(1, 0), idx;
 	std::vector<double> val, dinv(std::max(r1 - r0, 1), 1.0);
@@ -345,19 +589,60 @@ int pcg_setup(admmb_ctx *ctx) {
 	}
 	if (idx.empty()) { idx.push_back(0); val.push_back(0.0); }
 	const size_t npad = 3 * (size_t)ctx->chunk * ctx->dist_world;
+	// halo of the partitioned rows.  A_n is structurally symmetric, so "the owned nodes peer q's rows reference" is "the owned
+	// rows that reference a node of q": both sides derive the same sorted list from their own rows.
+	S.halo = ctx->dist_world > 1;
+	if (const char *e = getenv("ADMMB_PCG_HALO")) if (e[0] == '0') S.halo = false;
+	S.npad_nodes = (size_t)ctx->chunk * ctx->dist_world;
+	S.send_total = S.recv_total = 0;
+	if (S.halo) {
+		const int W = ctx->dist_world;
+		std::vector<std::vector<int> > recv(W), send(W);
+		for (int i = r0; i < r1; ++i)
+			for (int q = ctx->A_ptr[i]; q < ctx->A_ptr[i + 1]; ++q) {
+				const int j = ctx->A_idx[q];
+				if (j >= r0 && j < r1) continue;
+				const int o = j / ctx->chunk;
+				recv[o].push_back(j);
+				if (send[o].empty() || send[o].back() != i) send[o].push_back(i);
+			}
+		S.send_off.assign(W, 0); S.send_cnt.assign(W, 0); S.recv_off.assign(W, 0); S.recv_cnt.assign(W, 0);
+		std::vector<int> send_idx;
+		for (int o = 0; o < W; ++o) {
+			std::sort(recv[o].begin(), recv[o].end());
+			recv[o].erase(std::unique(recv[o].begin(), recv[o].end()), recv[o].end());
+			S.recv_off[o] = S.recv_total; S.recv_cnt[o] = (int)recv[o].size(); S.recv_total += S.recv_cnt[o];
+			S.send_off[o] = S.send_total; S.send_cnt[o] = (int)send[o].size(); S.send_total += S.send_cnt[o];
+			send_idx.insert(send_idx.end(), send[o].begin(), send[o].end());
+		}
+		std::vector<int> idxu(idx.size());
+		for (size_t e = 0; e < idx.size(); ++e) {
+			const int j = idx[e];
+			if ((j >= r0 && j < r1) || r1 <= r0) { idxu[e] = j; continue; }
+			const int o = j / ctx->chunk;
+			const int slot = S.recv_off[o] + (int)(std::lower_bound(recv[o].begin(), recv[o].end(), j) - recv[o].begin());
+			idxu[e] = (int)S.npad_nodes + slot;
+		}
+		if (send_idx.empty()) send_idx.push_back(0);
+		ADMMB_CUDA(ctx, S.idxu.upload(idxu, ctx->stream));
+		ADMMB_CUDA(ctx, S.send_idx.upload(send_idx, ctx->stream));
+		ADMMB_CUDA(ctx, S.send_buf.alloc(3 * (size_t)std::max(S.send_total, 1)));
+		if (getenv("ADMMB_VERBOSE")) fprintf(stderr, "[setup] rank %d: PCG halo: %d nodes sent, %d received per CG iteration (all-gather: %zu)\n", ctx->dist_rank, S.send_total, S.recv_total, S.npad_nodes);
+	}
 	ADMMB_CUDA(ctx, S.ptr.upload(ptr, ctx->stream));
 	ADMMB_CUDA(ctx, S.idx.upload(idx, ctx->stream));
 	ADMMB_CUDA(ctx, S.val.upload(val, ctx->stream));
 	ADMMB_CUDA(ctx, S.dinv.upload(dinv, ctx->stream));
 	ADMMB_CUDA(ctx, S.r.alloc(npad));
-	ADMMB_CUDA(ctx, S.u.alloc(npad));
+	ADMMB_CUDA(ctx, S.u.alloc(npad + 3 * (size_t)S.recv_total));
 	ADMMB_CUDA(ctx, S.w.alloc(npad));
 	ADMMB_CUDA(ctx, S.p.alloc(npad));
 	ADMMB_CUDA(ctx, S.s.alloc(npad));
 	ADMMB_CUDA(ctx, S.u.zero(ctx->stream));
 	ADMMB_CUDA(ctx, S.scal.alloc(S_SIZE));
-	ADMMB_CUDA(ctx, S.flag.alloc(4));
-	if (!S.h_flag) ADMMB_CUDA(ctx, cudaMallocHost((void **)&S.h_flag, 2 * sizeof(int)));
+	ADMMB_CUDA(ctx, S.flag.alloc(8));
+	ADMMB_CUDA(ctx, S.flag.zero(ctx->stream));
+	if (!S.h_flag) ADMMB_CUDA(ctx, cudaMallocHost((void **)&S.h_flag, 4 * sizeof(int)));
 	if (S.chunk_exec) { cudaGraphExecDestroy(S.chunk_exec); S.chunk_exec = nullptr; }
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -365,7 +650,7 @@ int pcg_setup(admmb_ctx *ctx) {
 	S.grid = want < sms * 4 ? (want > 0 ? want : 1) : sms * 4;
 	(void)n;
 	ADMMB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	return ADMMB_OK;
+	return pcg_p2p_setup(ctx, S);
 }
 
 // one CG iteration entering with the dots of parity q complete
@@ -373,10 +658,10 @@ static int pcg_enqueue_iteration(admmb_ctx *ctx, PcgSolver &S, int q, double tol
 	const int r0 = ctx->own0, r1 = ctx->own1;
 	cudaStream_t s = ctx->stream;
 	int rc;
-	k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q, S.dinv.p, S.u.p, S.w.p, S.p.p, S.s.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p, tol2);
-	if ((rc = dist_allgather_nodes(ctx, S.u.p))) return rc;
-	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q ^ 1, S.ptr.p, S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p);
-	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(q ^ 1), 9))) return rc;
+	k_pcg_update<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q, S.dinv.p, S.u.p, S.w.p, S.p.p, S.s.p, ctx->d_currx.p, S.r.p, S.scal.p, S.flag.p, tol2, S.peer);
+	if ((rc = pcg_exchange_u(ctx, S))) return rc;
+	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, q ^ 1, S.ptr.p, S.halo ? S.idxu.p : S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p, S.peer);
+	if (!S.p2p && (rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(q ^ 1), 9))) return rc;
 	ctx->launches += 2;
 	return ADMMB_OK;
 }
@@ -389,10 +674,10 @@ int pcg_solve(admmb_ctx *ctx) {
 	const double tol2 = tol * tol;
 	int rc;
 	ADMMB_CUDA(ctx, S.scal.zero(s));
-	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.u.p, S.p.p, S.s.p, S.scal.p, S.flag.p);
-	if ((rc = dist_allgather_nodes(ctx, S.u.p))) return rc;
-	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, 0, S.ptr.p, S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p);
-	if ((rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(0), 12))) return rc; // the dots of parity 0 and b.b
+	k_pcg_init<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, S.ptr.p, S.idx.p, S.val.p, S.dinv.p, ctx->d_b.p, ctx->d_currx.p, S.r.p, S.u.p, S.p.p, S.s.p, S.scal.p, S.flag.p, S.peer);
+	if ((rc = pcg_exchange_u(ctx, S))) return rc;
+	k_pcg_spmv<<<S.grid, PCG_THREADS, 0, s>>>(r0, r1, 0, S.ptr.p, S.halo ? S.idxu.p : S.idx.p, S.val.p, S.u.p, S.r.p, S.w.p, S.scal.p, S.flag.p, S.peer);
+	if (!S.p2p && (rc = dist_allreduce_sum(ctx, S.scal.p + S_DOTS(0), 12))) return rc; // the dots of parity 0 and b.b
 	ctx->launches += 2;
 	// chunk of PCG_CHUNK iterations (even: the parities repeat), captured once
 	if (!S.chunk_exec && !S.graph_failed && ctx->use_graph) {
@@ -415,11 +700,12 @@ int pcg_solve(admmb_ctx *ctx) {
 	S.h_flag[0] = 0; S.h_flag[1] = 0;
 	while (k < ctx->cg_max_iters) {
 		for (int c = 0; c < batch && k < ctx->cg_max_iters; ++c, k += PCG_CHUNK) {
-			if (S.chunk_exec) { ADMMB_CUDA(ctx, cudaGraphLaunch(S.chunk_exec, s)); ctx->launches += 2 * PCG_CHUNK; }
+			if (S.chunk_exec) { ADMMB_CUDA(ctx, cudaGraphLaunch(S.chunk_exec, s)); ctx->launches += (2 + ((S.halo && !S.p2p && S.send_total > 0) ? 1 : 0)) * PCG_CHUNK; }
 			else for (int i = 0; i < PCG_CHUNK; ++i) if ((rc = pcg_enqueue_iteration(ctx, S, i & 1, tol2))) return rc;
 		}
-		ADMMB_CUDA(ctx, cudaMemcpyAsync(S.h_flag, S.flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+		ADMMB_CUDA(ctx, cudaMemcpyAsync(S.h_flag, S.flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
 		ADMMB_CUDA(ctx, cudaStreamSynchronize(s));
+		if (S.h_flag[3]) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "PCG peer-to-peer exchange timed out waiting for another rank (rank %d)", ctx->dist_rank);
 		if (S.h_flag[0]) break;
 		batch = 1;
 	}
@@ -434,6 +720,9 @@ int pcg_solve(admmb_ctx *ctx) {
 void pcg_destroy(admmb_ctx *ctx) {
 	if (!ctx->pcg) return;
 	PcgSolver &S = *ctx->pcg;
+	pcg_p2p_teardown(ctx, S);
+	S.mail.free();
+	S.idxu.free(); S.send_idx.free(); S.send_buf.free();
 	S.ptr.free(); S.idx.free(); S.val.free(); S.dinv.free(); S.r.free(); S.u.free(); S.w.free(); S.p.free(); S.s.free(); S.scal.free(); S.flag.free();
 	if (S.chunk_exec) cudaGraphExecDestroy(S.chunk_exec);
 	if (S.h_flag) cudaFreeHost(S.h_flag);

@@ -33,11 +33,14 @@ sim.step_resident(frames=args.condition + args.warmup)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
+cg0 = sim.info()["cg_iters_total"]
 sim.step_resident(frames=args.steps)
 ms = sim.last_region_ms()
+cg1 = sim.info()["cg_iters_total"]
 sim.timing(True); sim.timing_read(reset=True)
 sim.step_resident(frames=max(2, args.steps // 2))
 ph = sim.timing_read(reset=True)
+cg2 = sim.info()["cg_iters_total"]
 sim.timing(False)
 ms_max, _ = ensemble.reduce_job(ms, 0)
 it = max(ph["iters"], 1)
@@ -46,6 +49,8 @@ if rank == 0:
     print(json.dumps({"cube": args.cube, "tets": int(sc["batches"][0]["idx"].shape[0]), "n_gpus": world, "solver": args.solver,
                       "value": args.steps * int(sc["iters"]) / (ms_max * 1e-3), "unit": "admm_iterations/s", "ms_per_iteration": ms_max / (args.steps * int(sc["iters"])),
                       "phases_ms_per_iteration_rank0": {"local": ph["local_ms"] / it, "rhs": ph["rhs_ms"] / it, "solve": ph["solve_ms"] / it},
+                      "timed_pass_ms_per_iteration_rank0": ph["step_ms"] / it,
+                      "cg_iterations_per_admm_iteration": [(cg1 - cg0) / float(args.steps * int(sc["iters"])), (cg2 - cg1) / float(it)],
                       "factor_bytes_rank0": info["factor_bytes"], "setup_s_rank0": t_setup}), flush=True)
 sim.close()
 if world > 1:
