@@ -546,7 +546,7 @@ def main():
         # global step: k_solve_level streams the packed factor once forward and once backward
         solve_bytes = info0["factor_bytes"] + 9 * nverts * 8 * 3  # factor tiles + b, y, x vectors read/written
         solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
-        roof_global = {"bound": "hbm", "kernel": f"k_solve_level_pf ({2 * info0['n_levels']} launches per solve)", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s",
+        roof_global = {"bound": "hbm", "kernel": f"{'k_solve_level_pf' if os.environ.get('ADMMB_SOLVE_MODE') == '3' else 'k_solve_level_tma'} ({2 * info0['n_levels']} launches per solve, programmatic dependent launch chain)", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": solve_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "share_of_step": solve_ms / phase_sum,
                        "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; {info0['n_levels']} levels; "
                                "ncu dram traffic of the same launches: profiles/ (1.03x the algorithmic bytes at N=55)"}

@@ -6,7 +6,9 @@
   slots in the same order as on one GPU, so with the deterministic solve the partitioned run must reproduce the single-GPU run
   BIT FOR BIT (positions, and z / u / optimiser state merged from the ranks' exports); with the default (atomic) solve the ranks
   must still agree with each other bit for bit (their solution chunks are exchanged) and with one GPU to rounding.
-* PCG: partitioned rows, NCCL all-gather / all-reduce per CG iteration; every rank must reproduce the single-GPU PCG result.
+* PCG: partitioned rows; the halo of the preconditioned residual and the partial dot products are exchanged peer to peer inside
+  the CG kernels (or through NCCL: fallback modes, forced here through the environment); every rank must reproduce the single-GPU
+  PCG result, and the ranks must agree bit for bit.
 """
 import multiprocessing as mp
 
@@ -54,19 +56,33 @@ def _single(kw, frames, solver, deterministic):
     return out
 
 
-def _two_ranks(kw, frames, solver, deterministic):
+def _ranks(world, kw, frames, solver, deterministic, env=None):
+    import os
     import admm_b200
     uid = admm_b200.dist_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, uid, kw, frames, solver, deterministic, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})          # spawned workers inherit the parent's environment
+    try:
+        procs = [ctx.Process(target=_worker, args=(r, world, uid, kw, frames, solver, deterministic, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     return res
+
+
+def _two_ranks(kw, frames, solver, deterministic, env=None):
+    return _ranks(2, kw, frames, solver, deterministic, env)
 
 
 def _need_two():
@@ -119,18 +135,50 @@ def test_two_rank_direct_default_solve_ranks_identical(N):
     assert err <= 1e-9   # ARAP is reproducible in the reference: north_star's per-iteration gate
 
 
+# how the partitioned PCG rows exchange: peer-to-peer stores inside the CG kernels (default), NCCL grouped send / receive of
+# the halo + all-reduce (the fallback), all-gather of the whole vector + all-reduce (round 1)
+PCG_EXCHANGE = {"p2p": {}, "nccl_halo": {"ADMMB_PCG_P2P": "0"}, "allgather": {"ADMMB_PCG_HALO": "0"}}
+
+
+@pytest.mark.parametrize("exchange", list(PCG_EXCHANGE))
 @pytest.mark.parametrize("kind,label", [(scenes.TET_ARAP, "arap"), (scenes.TET_NH, "nh")])
-def test_two_rank_pcg_matches_single_gpu(kind, label):
+def test_two_rank_pcg_matches_single_gpu(kind, label, exchange):
     _need_two()
     import admm_b200
     kw = dict(N=8, kind=kind, seed=31)
     frames = 3
     xr = _single(kw, frames, admm_b200.SOLVER_PCG, False)[0]
-    res = _two_ranks(kw, frames, admm_b200.SOLVER_PCG, False)
+    res = _two_ranks(kw, frames, admm_b200.SOLVER_PCG, False, PCG_EXCHANGE[exchange])
     x0, x1 = res[0][1], res[1][1]
     same = np.array_equal(x0, x1)
     err = max(np.linalg.norm(x0[f] - xr[f]) / np.linalg.norm(xr[f]) for f in range(len(xr)))
-    print(f"{label}: ranks identical: {same}; 2-rank vs 1-GPU PCG rel-L2 {err:.2e}; CG iterations {res[0][2]}")
+    print(f"{label} / {exchange}: ranks identical: {same}; 2-rank vs 1-GPU PCG rel-L2 {err:.2e}; CG iterations {res[0][2]}")
     assert same
     # NH: the reference algorithm itself amplifies the CG tolerance (1e-13) to ~1e-5 within a few frames; ARAP does not
     assert err <= (1e-9 if kind == scenes.TET_ARAP else 1e-3)
+
+
+def _all_gpus():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 4:
+        pytest.skip("needs at least four CUDA devices (gpurun --gpus 4 / 8)")
+    return min(n, 8)
+
+
+@pytest.mark.parametrize("solver", ["direct", "pcg"])
+def test_many_ranks_match_single_gpu(solver):
+    """The same on every GPU of the box (4 or 8 ranks): several peers per rank in the PCG halo / mailboxes, a deeper cut of
+    the elimination tree in the sharded direct solve.  ARAP, so the 1e-9 gate applies."""
+    world = _all_gpus()
+    import admm_b200
+    kw = dict(N=16, kind=scenes.TET_ARAP, seed=31)
+    frames = 3
+    sv = admm_b200.SOLVER_PCG if solver == "pcg" else admm_b200.SOLVER_DIRECT
+    xr = _single(kw, frames, sv, False)[0]
+    res = _ranks(world, kw, frames, sv, False)
+    for r in range(1, world):
+        assert np.array_equal(res[0][1], res[r][1]), f"rank {r} differs from rank 0"
+    err = max(np.linalg.norm(res[0][1][f] - xr[f]) / np.linalg.norm(xr[f]) for f in range(len(xr)))
+    print(f"{world}-rank {solver} vs 1 GPU rel-L2 {err:.2e}")
+    assert err <= 1e-9
