@@ -237,10 +237,12 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
 	asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-// bounded spin (about a second): a peer that never arrives sets flag[3] and lets the kernels drain instead of hanging the GPU
+// bounded spin (2^28 polls of >= 64 ns: 20-30 s, far beyond any host-side stall between two ranks' launches): a peer that
+// never arrives sets flag[3], which makes every later wait return at once, so the kernels drain and the host reports an
+// error instead of the GPU hanging
 __device__ __noinline__ void peer_wait(const int *word, int want, int *flag) {
 	if (flag[3]) return;
-	for (int spin = 0; spin < (1 << 24); ++spin) {
+	for (int spin = 0; spin < (1 << 28); ++spin) {
 		if (ld_acquire_sys(word) >= want) return;
 		__nanosleep(64);
 	}
