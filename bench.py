@@ -487,8 +487,10 @@ def main():
     # the three phases of every iteration, as many frames as the timed region
     sim.timing(True)
     sim.timing_read(reset=True)
+    cg_before_phases = sim.info()["cg_iters_total"]
     sim.step_resident(frames=args.steps)
     phases = sim.timing_read(reset=True)
+    cg_phases_pass = (sim.info()["cg_iters_total"] - cg_before_phases) / float(max(phases["iters"], 1))
     sim.timing(False)
     flops = algorithmic_flops_per_tet(sim, sc) if (hyper and rank == 0) else None
 
@@ -570,7 +572,10 @@ def main():
             "clocks": clocks,
             "phases_ms_per_iteration": {"local": local_ms, "rhs": rhs_ms, "solve": solve_ms, "sum": phase_sum, "step": step_ms,
                                         "note": "phases: CUDA events around each phase in a second pass of --steps frames in the same (conditioned) regime; "
-                                                "step = ms_per_step / iterations of the timed region itself"},
+                                                "step = ms_per_step / iterations of the timed region itself"
+                                                + ("; PCG: the CG iteration count falls as the scene settles, so the solve phase of the (later) phase pass is "
+                                                   "cheaper than the timed region's -- cg_iterations_per_admm_iteration gives both" if args.solver == "pcg" else ""),
+                                        "cg_iterations_per_admm_iteration": cg_phases_pass if args.solver == "pcg" else None},
             "setup": {"seconds": t_setup, "factor_seconds": info0["factor_seconds"], "nnz_L": info0["nnz_L"],
                       "supernodes": info0["n_supernodes"], "levels": info0["n_levels"], "factor_bytes": info0["factor_bytes"]},
         }
