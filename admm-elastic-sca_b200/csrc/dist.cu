@@ -130,10 +130,10 @@ int dist_allgather_host(admmb_ctx *ctx, const void *mine, void *all, size_t byte
 	if (ctx->dist_world == 1) { memcpy(all, mine, bytes); return ADMMB_OK; }
 	DevBuf<char> d;
 	ADMMB_CUDA(ctx, d.alloc(bytes * ctx->dist_world));
-	ADMMB_CUDA(ctx, cudaMemcpyAsync(d.p + bytes * ctx->dist_rank, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	ncclResult_t r = g_nccl.AllGather(d.p + bytes * ctx->dist_rank, d.p, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream);
-	cudaError_t e = cudaSuccess;
-	if (r == ncclSuccess) e = cudaMemcpyAsync(all, d.p, bytes * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->stream);
+	cudaError_t e = cudaMemcpyAsync(d.p + bytes * ctx->dist_rank, mine, bytes, cudaMemcpyHostToDevice, ctx->stream);
+	ncclResult_t r = ncclSuccess;
+	if (e == cudaSuccess) r = g_nccl.AllGather(d.p + bytes * ctx->dist_rank, d.p, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+	if (r == ncclSuccess && e == cudaSuccess) e = cudaMemcpyAsync(all, d.p, bytes * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->stream);
 	if (r == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	d.free();
 	if (r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "ncclAllGather -> %s", g_nccl.GetErrorString(r));
@@ -148,10 +148,10 @@ int dist_allreduce_host_int(admmb_ctx *ctx, int *value) {
 	ADMMB_CUDA(ctx, d.alloc(1));
 	const double v = (double)*value;
 	double out = 0.0;
-	ADMMB_CUDA(ctx, cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-	ncclResult_t r = g_nccl.AllReduce(d.p, d.p, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
-	cudaError_t e = cudaSuccess;
-	if (r == ncclSuccess) e = cudaMemcpyAsync(&out, d.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	cudaError_t e = cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+	ncclResult_t r = ncclSuccess;
+	if (e == cudaSuccess) r = g_nccl.AllReduce(d.p, d.p, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+	if (r == ncclSuccess && e == cudaSuccess) e = cudaMemcpyAsync(&out, d.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
 	if (r == ncclSuccess && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	d.free();
 	if (r != ncclSuccess) ADMMB_FAIL(ctx, ADMMB_E_CUDA, "ncclAllReduce -> %s", g_nccl.GetErrorString(r));
