@@ -137,11 +137,11 @@ def load_workload(name):
     return sc, f"samples/{name} ({nel} elements, {sc['x'].shape[0]} nodes), {sc['iters']} ADMM iterations per step, dt {sc['dt']}, no user interaction"
 
 
-def reference_rate(sc, frames, cond):
+def reference_rate(sc, frames, cond, threads=None):
     """ADMM iterations/s of the UNMODIFIED reference (oracle/_ref: Eigen + OpenMP on all host cores) on scene `sc`:
     `cond` untimed frames, then `frames` timed with std::chrono inside the shim (System::step only)."""
     from oracle import ref
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     ref.lib().ref_set_omp_threads(cores)
     t0 = time.perf_counter()
     sim = ref.RefSystem(sc, probe=False)
@@ -268,9 +268,16 @@ def cpu_baseline_leg(N):
     ntets = sc["batches"][0]["idx"].shape[0]
     frames = 8
     r = reference_rate(sc, frames, CONDITION_FRAMES)
+    # SURVEY 8(d) asks for OMP_NUM_THREADS=1 beside all cores: a smaller sample of the same workload keeps it to a few seconds
+    N1 = min(N, 12)
+    sc1 = make_scene(N1)
+    ntets1 = sc1["batches"][0]["idx"].shape[0]
+    r1 = reference_rate(sc1, frames, CONDITION_FRAMES, threads=1)
     return {"value": r["it_s"] * ntets / FULL_TETS, "unit": UNIT, "cores": r["cores"], "kind": "reference",
             "sample": f"unmodified reference (Eigen + OpenMP, {r['cores']} threads) on cube N={N} ({ntets} tets): {r['it_s']:.2f} it/s over {frames} frames after "
-                      f"{CONDITION_FRAMES} untimed frames, scaled x{ntets}/{FULL_TETS}; initialize() {r['init_s']:.1f} s excluded"}
+                      f"{CONDITION_FRAMES} untimed frames, scaled x{ntets}/{FULL_TETS}; initialize() {r['init_s']:.1f} s excluded",
+            "one_thread": {"value": r1["it_s"] * ntets1 / FULL_TETS, "unit": UNIT, "cores": 1,
+                           "sample": f"the same with 1 thread on cube N={N1} ({ntets1} tets): {r1['it_s']:.2f} it/s over {frames} frames, scaled x{ntets1}/{FULL_TETS}"}}
 
 
 def algorithmic_flops_per_tet(sim, sc, sample=4096, seed=12345):
