@@ -27,6 +27,7 @@
 
 #include "common.h"
 #include "direct_factor.h"
+#include "dist_plan.h"
 
 namespace admmb {
 
@@ -433,72 +434,6 @@ static void fill_backward(const TilePlan &p, double *dst) {
 	for (int i = 0; i < t.ncols; ++i)
 		for (int k = 0; k < t.nrows; ++k) dst[(size_t)i * t.nrows + k] = p.src[(p.lo + i) + (size_t)(p.k0 + k) * p.m];
 	for (size_t i = (size_t)t.nrows * t.ncols; i < align16((size_t)t.nrows * t.ncols); ++i) dst[i] = 0.0;
-}
-
-// Subtree-to-rank mapping of the supernodal elimination tree (the classic way to parallelise a sparse triangular solve):
-// the tree is cut near its root; everything above the cut (the largest separators) is processed by EVERY rank, each
-// subtree below it by ONE rank.  Subtrees only couple through the rows of their common ancestors, so the forward pass
-// needs one all-reduce of those (few) rows and the backward pass none.  The cut is chosen by repeatedly opening the
-// heaviest subtree and keeping the configuration that minimises (replicated bytes + heaviest rank's bytes), the
-// bandwidth cost of the slowest rank.  owner[J] = rank, or -1 for the replicated top.
-static std::vector<int> shard_owners(const SupernodalFactor &F, int world, double *top_fraction) {
-	const int nb = F.nb;
-	std::vector<double> wgt(nb), sub(nb, 0.0);
-	std::vector<std::vector<int> > kids(nb);
-	double total = 0.0;
-	for (int J = 0; J < nb; ++J) {
-		const double w = F.start[J + 1] - F.start[J], r = F.rptr[J + 1] - F.rptr[J];
-		wgt[J] = (w + r) * w;
-		total += wgt[J];
-	}
-	for (int J = 0; J < nb; ++J) { // children precede their parents in elimination order
-		sub[J] += wgt[J];
-		if (F.parent[J] >= 0) { sub[F.parent[J]] += sub[J]; kids[F.parent[J]].push_back(J); }
-	}
-	std::vector<char> is_top(nb, 0);
-	std::vector<int> cand;
-	for (int J = 0; J < nb; ++J) if (F.parent[J] < 0) cand.push_back(J);
-	auto lpt = [&](const std::vector<int> &c, std::vector<int> *assign) {
-		std::vector<int> order(c);
-		std::sort(order.begin(), order.end(), [&](int a, int b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
-		std::vector<double> load(world, 0.0);
-		if (assign) assign->assign(nb, -2);
-		for (int J : order) {
-			int r = 0;
-			for (int q = 1; q < world; ++q) if (load[q] < load[r]) r = q;
-			load[r] += sub[J];
-			if (assign) (*assign)[J] = r;
-		}
-		return *std::max_element(load.begin(), load.end());
-	};
-	double top_w = 0.0, best = 1e300;
-	std::vector<char> best_top;
-	std::vector<int> best_cand;
-	for (int it = 0; it < 64 * world; ++it) {
-		const double cost = top_w + lpt(cand, nullptr);
-		if ((int)cand.size() >= world && cost < best) { best = cost; best_top = is_top; best_cand = cand; }
-		int h = -1;
-		for (size_t i = 0; i < cand.size(); ++i) if (!kids[cand[i]].empty() && (h < 0 || sub[cand[i]] > sub[cand[h]])) h = (int)i;
-		if (h < 0) break;
-		const int J = cand[h];
-		is_top[J] = 1;
-		top_w += wgt[J];
-		cand.erase(cand.begin() + h);
-		cand.insert(cand.end(), kids[J].begin(), kids[J].end());
-	}
-	std::vector<int> owner(nb, -1);
-	if (best_cand.empty()) { if (top_fraction) *top_fraction = 1.0; return owner; } // cannot be cut: everything replicated
-	std::vector<int> assign;
-	lpt(best_cand, &assign);
-	for (int J = nb - 1; J >= 0; --J) { // parents before children
-		if (best_top[J]) owner[J] = -1;
-		else if (assign[J] >= 0) owner[J] = assign[J];
-		else owner[J] = (F.parent[J] >= 0) ? owner[F.parent[J]] : 0;
-	}
-	double tw = 0.0;
-	for (int J = 0; J < nb; ++J) if (owner[J] < 0) tw += wgt[J];
-	if (top_fraction) *top_fraction = total > 0.0 ? tw / total : 1.0;
-	return owner;
 }
 
 __global__ void k_rows_zero(int cnt, const int *__restrict__ rows, double *v) {

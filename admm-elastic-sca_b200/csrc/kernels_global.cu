@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "dist_plan.h"
 
 namespace admmb {
 
@@ -598,32 +599,16 @@ int pcg_setup(admmb_ctx *ctx) {
 	S.npad_nodes = (size_t)ctx->chunk * ctx->dist_world;
 	S.send_total = S.recv_total = 0;
 	if (S.halo) {
-		const int W = ctx->dist_world;
-		std::vector<std::vector<int> > recv(W), send(W);
-		for (int i = r0; i < r1; ++i)
-			for (int q = ctx->A_ptr[i]; q < ctx->A_ptr[i + 1]; ++q) {
-				const int j = ctx->A_idx[q];
-				if (j >= r0 && j < r1) continue;
-				const int o = j / ctx->chunk;
-				recv[o].push_back(j);
-				if (send[o].empty() || send[o].back() != i) send[o].push_back(i);
-			}
-		S.send_off.assign(W, 0); S.send_cnt.assign(W, 0); S.recv_off.assign(W, 0); S.recv_cnt.assign(W, 0);
-		std::vector<int> send_idx;
-		for (int o = 0; o < W; ++o) {
-			std::sort(recv[o].begin(), recv[o].end());
-			recv[o].erase(std::unique(recv[o].begin(), recv[o].end()), recv[o].end());
-			S.recv_off[o] = S.recv_total; S.recv_cnt[o] = (int)recv[o].size(); S.recv_total += S.recv_cnt[o];
-			S.send_off[o] = S.send_total; S.send_cnt[o] = (int)send[o].size(); S.send_total += S.send_cnt[o];
-			send_idx.insert(send_idx.end(), send[o].begin(), send[o].end());
-		}
+		HaloPlan H;
+		plan_halo(ctx->A_ptr.data(), ctx->A_idx.data(), ctx->chunk, ctx->dist_world, r0, r1, H);
+		S.send_off = H.send_off; S.send_cnt = H.send_cnt; S.recv_off = H.recv_off; S.recv_cnt = H.recv_cnt;
+		S.send_total = H.send_total; S.recv_total = H.recv_total;
+		std::vector<int> send_idx = H.send_idx;
 		std::vector<int> idxu(idx.size());
 		for (size_t e = 0; e < idx.size(); ++e) {
 			const int j = idx[e];
 			if ((j >= r0 && j < r1) || r1 <= r0) { idxu[e] = j; continue; }
-			const int o = j / ctx->chunk;
-			const int slot = S.recv_off[o] + (int)(std::lower_bound(recv[o].begin(), recv[o].end(), j) - recv[o].begin());
-			idxu[e] = (int)S.npad_nodes + slot;
+			idxu[e] = (int)S.npad_nodes + H.slot_of(j, ctx->chunk);
 		}
 		if (send_idx.empty()) send_idx.push_back(0);
 		ADMMB_CUDA(ctx, S.idxu.upload(idxu, ctx->stream));
