@@ -24,6 +24,7 @@ if world > 1:
     holder = [admm_b200.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(holder, src=0)
     dist_arg = (rank, world, holder[0])
+admm_b200.lib().admmb_set_host_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun exports OMP_NUM_THREADS=1: give the set-up its share of the cores
 sc = scenes.cube_scene(args.cube, kind=scenes.TET_NH, mu=1e5, lam=1e5, maxit=5, mass=1000.0, dt=0.04, iters=10, stretch=1.3)
 t0 = time.perf_counter()
 sim = admm_b200.System(sc, device=local, solver=admm_b200.SOLVER_DIRECT if args.solver == "direct" else admm_b200.SOLVER_PCG, cg_tol=1e-10, dist=dist_arg)
