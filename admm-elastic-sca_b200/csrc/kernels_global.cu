@@ -361,8 +361,11 @@ __global__ void __launch_bounds__(PCG_THREADS) k_pcg_init(int r0, int n, const i
 }
 
 // w = A u; dots[q] += (r.u, w.u, r.r)
+// (u is deliberately NOT `const __restrict__`: on a partitioned mesh its halo slots are written by the peers while this kernel
+// is already resident -- before wait_halo returns -- so its loads must not take the non-coherent LDG.CONSTANT path, whose
+// contract is "unchanged for the lifetime of the kernel" and which the compiler may hoist above the wait)
 __global__ void __launch_bounds__(PCG_THREADS) k_pcg_spmv(int r0, int n, int q, const int *__restrict__ ptr, const int *__restrict__ idx,
-                                                          const double *__restrict__ val, const double *__restrict__ u,
+                                                          const double *__restrict__ val, const double *u,
                                                           const double *__restrict__ r, double *__restrict__ w, double *scal, int *flag, const PeerArgs P) {
 	if (flag[0]) return;
 	wait_halo(P, flag);
