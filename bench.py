@@ -260,6 +260,36 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def committed_traffic(cube):
+    """DRAM bytes per launch (local-step kernel) and per solve (its 26 launches) from the ncu --set full captures of the
+    round's final build committed under profiles/ (r2_local.txt, r2_solve.txt: cube N=55).  Not measured in this run -- ncu
+    cannot run inside the timed bench -- so the values carry their source, and any other workload gets None."""
+    out = {"local": None, "solve": None}
+    if cube != 55:
+        return out
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    try:
+        rd = wr = None
+        for ln in open(os.path.join(root, "r2_local.txt")):
+            t = ln.split()
+            if len(t) == 2 and t[0] == "dram__bytes_read.sum":
+                rd = float(t[1])
+            if len(t) == 2 and t[0] == "dram__bytes_write.sum":
+                wr = float(t[1])
+        if rd is not None and wr is not None:
+            out["local"] = (rd + wr) * 1e6
+    except (OSError, ValueError):
+        pass
+    try:
+        import re
+        m = re.search(r"DRAM traffic ([0-9.]+) MB", open(os.path.join(root, "r2_solve.txt")).read())
+        if m:
+            out["solve"] = float(m.group(1)) * 1e6
+    except (OSError, ValueError):
+        pass
+    return out
+
+
 def cpu_baseline_leg(N):
     from oracle import ref
     if not ref.available():
@@ -552,11 +582,14 @@ def main():
         rhs_ms = phases["rhs_ms"] / iters
         phase_sum = local_ms + rhs_ms + solve_ms
         step_ms = ms_region_max / args.steps / iters_per_frame
+        traffic = committed_traffic(args.cube if (not args.scene and args.solver == "direct") else None)
         # global step: k_solve_level streams the packed factor once forward and once backward
         solve_bytes = info0["factor_bytes"] + 9 * nverts * 8 * 3  # factor tiles + b, y, x vectors read/written
         solve_gbs = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
         roof_global = {"bound": "hbm", "kernel": f"{'k_solve_level_pf' if os.environ.get('ADMMB_SOLVE_MODE') == '3' else 'k_solve_level_tma'} ({2 * info0['n_levels']} launches per solve, programmatic dependent launch chain)", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": solve_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "share_of_step": solve_ms / phase_sum,
+                       "frac": solve_gbs / hbm_peak, "traffic": traffic["solve"],
+                       "traffic_note": "bytes per solve (all its launches), dram__bytes_read + write of the committed ncu --set full capture profiles/r2_solve.txt (final build of the round, same workload); algorithmic bytes per solve: %d" % int(solve_bytes) if traffic["solve"] else None,
+                       "peak_source": peak_src, "share_of_step": solve_ms / phase_sum,
                        "note": f"algorithmic bytes per solve = packed factor, both copies ({info0['factor_bytes']} B) + 9 vector passes of 3n doubles; {info0['n_levels']} levels; "
                                "ncu dram traffic of the same launches: profiles/ (1.03x the algorithmic bytes at N=55)"}
         line = {
@@ -595,7 +628,9 @@ def main():
             alg = flops["flops_per_tet_iteration"] * ntets / (local_ms * 1e-3) / 1e12 if local_ms > 0 else 0.0
             line["roofline"] = {
                 "bound": "fp64", "kernel": "k_local_tets_hyper<NHModel,5> (1 launch per ADMM iteration)", "achieved": alg, "peak": peak_fma, "unit": "TFLOP/s",
-                "frac": alg / peak_fma, "traffic": None, "share_of_step": local_ms / phase_sum,
+                "frac": alg / peak_fma, "traffic": traffic["local"],
+                "traffic_note": "bytes per launch, dram__bytes_read + write of the committed ncu --set full capture profiles/r2_local.txt (final build of the round, same workload); algorithmic bytes per launch: %d" % (LOCAL_BYTES_PER_TET * ntets) if traffic["local"] else None,
+                "share_of_step": local_ms / phase_sum,
                 "peak_source": "admmb_probe_fp64 on this device in this run: independent DFMA chains, 2 flops each (of measured)",
                 "frac_of_unfused_peak": alg / peak_nofma, "unfused_peak": peak_nofma,
                 "algorithmic_flops_per_tet_iteration": flops["flops_per_tet_iteration"], "flop_count": flops,
