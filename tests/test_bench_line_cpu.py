@@ -144,3 +144,23 @@ def test_reference_arm_line(bench, monkeypatch):
     assert d["impl"] == "reference" and d["metric"] == "admm_iterations_per_s_cube_1M_tets" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == pytest.approx(d["value"])
     assert d["e2e"]["value"] == pytest.approx(d["value"]) and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_multi_rank_line_has_the_partition_object(bench, monkeypatch):
+    """Rank 0 of a (faked) 2-rank torchrun job: the replica ensemble is `value`, ONE mesh partitioned over the ranks is `partition`."""
+    import torch.distributed as dist
+    monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("RANK", "0"); monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None, raising=False)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "broadcast_object_list", lambda obj, src=0: None)
+    fake = sys.modules["admm_b200"]
+    fake.lib = lambda: types.SimpleNamespace(admmb_set_host_threads=lambda n: 0)
+    fake.dist_unique_id = lambda: b"\0" * 128
+    d = _run(bench, monkeypatch, ["--gpus", "2", "--steps", "3", "--warmup", "3", "--no-pairs"])
+    for k in BASE_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and "cpu_baseline" not in d
+    p = d["partition"]
+    assert p["scaling"] == "strong" and p["value"] > 0 and p["unit"] == d["unit"]
+    assert set(["local", "rhs_and_allgather", "solve_and_allreduce"]) == set(p["phases_ms_per_iteration_rank0"])
